@@ -1,0 +1,46 @@
+"""impdar_b200 - B200 (sm_100a) backend for ImpDAR's radargram migration + filtering hot path.
+
+    import impdar_b200
+    impdar_b200.install()          # rebinds impdar.lib.migrationlib.* and the RadarData filter methods
+    dat.migrate(mtype='kirch')     # unchanged ImpDAR call, now running on the GPU
+
+or, without ImpDAR installed, ``impdar_b200.RadarData`` offers the same hot-path methods.
+"""
+from . import migrationlib, filtering  # noqa: F401
+from .radardata import RadarData, RadarFlags  # noqa: F401
+from .migrationlib import (migrationKirchhoff, migrationStolt, migrationPhaseShift,  # noqa: F401
+                           migrationTimeWavenumber, getVelocityProfile)
+
+__version__ = "0.1.0"
+
+_MIGRATION_NAMES = ('migrationKirchhoff', 'migrationStolt', 'migrationPhaseShift', 'migrationTimeWavenumber')
+_FILTER_NAMES = ('vertical_band_pass', 'horizontalfilt', 'adaptivehfilt')
+_saved = {}
+
+
+def install():
+    """Bind the backend behind the reference's seam: the four migration callables on the
+    ``impdar.lib.migrationlib`` module (looked up by RadarData.migrate at call time,
+    _RadarDataFiltering.py:610-631) and vertical_band_pass / horizontalfilt / adaptivehfilt on the RadarData
+    class (RadarData/__init__.py:119-121).  mtype 'su*' keeps routing to the reference's SeisUnix shim."""
+    import impdar.lib.migrationlib as ref_mig
+    from impdar.lib.RadarData import RadarData as RefRadarData
+    if _saved:
+        return
+    for name in _MIGRATION_NAMES:
+        _saved[('mig', name)] = getattr(ref_mig, name)
+        setattr(ref_mig, name, getattr(migrationlib, name))
+    for name in _FILTER_NAMES:
+        _saved[('rd', name)] = getattr(RefRadarData, name)
+        setattr(RefRadarData, name, getattr(filtering, name))
+
+
+def uninstall():
+    """Restore the reference's own callables."""
+    if not _saved:
+        return
+    import impdar.lib.migrationlib as ref_mig
+    from impdar.lib.RadarData import RadarData as RefRadarData
+    for (kind, name), fn in list(_saved.items()):
+        setattr(ref_mig if kind == 'mig' else RefRadarData, name, fn)
+    _saved.clear()

@@ -1,0 +1,130 @@
+// Library-level plumbing: error string, launch counter, and the HOST-pointer entry points
+// (the reference's own C prototype mig_kirch_loop, migrationlib/mig_cython.h:11).
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <atomic>
+#include <vector>
+
+#include "common.cuh"
+
+namespace impdar {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// np.gradient(f, x, axis=0) stencil rows a, b, c (numpy/lib/_function_base_impl.py gradient, edge_order=1):
+// uniform spacing (all diffs equal) -> central difference over 2h that never touches f[i]; otherwise the
+// second-order non-uniform formula.  Returns false when numpy would raise (fewer than 2 samples).
+static bool gradient_coefficients(const double *x, int n, std::vector<double> &coef) {
+    if (n < 2) return false;
+    coef.assign((size_t)3 * n, 0.0);
+    double *a = coef.data(), *b = a + n, *c = b + n;
+    bool uniform = true;
+    const double h0 = x[1] - x[0];
+    for (int i = 1; i < n - 1; ++i)
+        if ((x[i + 1] - x[i]) != h0) { uniform = false; break; }
+    for (int i = 1; i < n - 1; ++i) {
+        if (uniform) {
+            a[i] = -1.0 / (2.0 * h0);
+            c[i] = 1.0 / (2.0 * h0);
+        } else {
+            const double d1 = x[i] - x[i - 1], d2 = x[i + 1] - x[i];
+            a[i] = -(d2) / (d1 * (d1 + d2));
+            b[i] = (d2 - d1) / (d1 * d2);
+            c[i] = d1 / (d2 * (d1 + d2));
+        }
+    }
+    const double hf = x[1] - x[0], hl = x[n - 1] - x[n - 2];
+    b[0] = -1.0 / hf; c[0] = 1.0 / hf;
+    a[n - 1] = -1.0 / hl; b[n - 1] = 1.0 / hl;
+    return true;
+}
+
+static int kirchhoff_host(const double *src, bool src_is_gradient, double *migdata, int S, int T,
+                          const double *dist_m, const double *tt_s, double vel, int nearfield) {
+    IMPDAR_CHECK_ARG(src && migdata && dist_m && tt_s, "kirchhoff_host: null pointer");
+    IMPDAR_CHECK_ARG(S >= 2 && T >= 1, "kirchhoff_host: need snum >= 2 and tnum >= 1");
+    std::vector<double> coef;
+    if (src_is_gradient) {
+        coef.assign((size_t)3 * S, 0.0);
+        for (int i = 0; i < S; ++i) coef[(size_t)S + i] = 1.0;  // identity stencil: the input already is dD/dt
+    } else {
+        IMPDAR_CHECK_ARG(gradient_coefficients(tt_s, S, coef), "kirchhoff_host: gradient needs >= 2 samples");
+    }
+    const size_t n = (size_t)S * T;
+    std::vector<float> h32(n);
+    for (size_t i = 0; i < n; ++i) h32[i] = (float)src[i];
+    float *d_in = nullptr, *d_out = nullptr;
+    void *ws = nullptr;
+    const size_t wsb = impdar_kirchhoff_workspace_bytes(S, T, nearfield);
+    int rc = IMPDAR_B200_OK;
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&d_in, n * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&d_out, n * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&ws, wsb)) != cudaSuccess) {
+        set_error("kirchhoff_host: cudaMalloc -> %s", cudaGetErrorString(e));
+        rc = IMPDAR_B200_ECUDA;
+    }
+    if (!rc && (e = cudaMemcpy(d_in, h32.data(), n * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        set_error("kirchhoff_host: H2D -> %s", cudaGetErrorString(e));
+        rc = IMPDAR_B200_ECUDA;
+    }
+    if (!rc) rc = impdar_kirchhoff_f32(d_in, d_out, S, T, dist_m, tt_s, coef.data(), vel, nearfield, 0, T, ws, wsb, nullptr);
+    if (!rc && (e = cudaMemcpy(h32.data(), d_out, n * sizeof(float), cudaMemcpyDeviceToHost)) != cudaSuccess) {
+        set_error("kirchhoff_host: D2H -> %s", cudaGetErrorString(e));
+        rc = IMPDAR_B200_ECUDA;
+    }
+    if (!rc)
+        for (size_t i = 0; i < n; ++i) migdata[i] = (double)h32[i];
+    cudaFree(d_in);
+    cudaFree(d_out);
+    cudaFree(ws);
+    return rc;
+}
+
+}  // namespace impdar
+
+using namespace impdar;
+
+extern "C" {
+
+int impdar_b200_version(void) { return 100; }
+const char *impdar_b200_last_error(void) { return g_err; }
+unsigned long long impdar_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int impdar_kirchhoff_host_f64(const double *data, double *migdata, int S, int T, const double *dist_m,
+                              const double *tt_s, double vel, int nearfield) {
+    return kirchhoff_host(data, false, migdata, S, T, dist_m, tt_s, vel, nearfield);
+}
+
+void mig_kirch_loop(double *migdata, int tnum, int snum, double *dist, double *zs, double *zs2, double *tt_sec,
+                    double vel, double *gradD, double max_travel_time, int nearfield) {
+    (void)zs;
+    (void)zs2;
+    (void)max_travel_time;  // recomputed on the device from tt_sec and vel with the same expressions
+    int rc;
+    if (nearfield) {
+        set_error("mig_kirch_loop: the reference prototype carries no data pointer, the near-field term needs "
+                  "impdar_kirchhoff_host_f64");
+        rc = IMPDAR_B200_EINVAL;
+    } else {
+        rc = kirchhoff_host(gradD, true, migdata, snum, tnum, dist, tt_sec, vel, 0);
+    }
+    if (rc && migdata) {
+        const size_t n = (size_t)snum * (size_t)tnum;
+        for (size_t i = 0; i < n; ++i) migdata[i] = NAN;
+        fprintf(stderr, "impdar_b200: mig_kirch_loop failed: %s\n", g_err);
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,488 @@
+// Filtering kernels: taper, horizontalfilt, adaptivehfilt, filtfilt (vertical_band_pass), FIR lfilter.
+// Reference semantics: RadarData/_RadarDataFiltering.py (line numbers in include/impdar_b200.h).
+// All of these are HBM-bound: traces are the contiguous axis, so every kernel maps lanes to traces
+// (coalesced 128-bit accesses) and keeps per-row / per-trace state on chip.
+#include "common.cuh"
+
+namespace impdar {
+
+// --------------------------------------------------------------------------------------------- taper
+__device__ __forceinline__ double taper_weight(int i, int n, double len) {
+    int m = min(i, n - 1 - i);
+    double w = (double)m / len;  // 0/0 -> NaN, m/0 -> inf -> clipped to 1, like numpy
+    if (w > 1.0) w = 1.0;
+    return w;
+}
+
+__global__ void __launch_bounds__(256) taper_kernel(const float *__restrict__ x, float *__restrict__ y, int S,
+                                                    int T, long long rows, double htaper, double vtaper,
+                                                    int trunc_int) {
+    // one row per blockIdx.y-stride, columns vectorised by 4 when possible
+    const bool vec = ((T & 3) == 0) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int s = (int)(row % S);
+        const double v = taper_weight(s, S, vtaper);
+        const float *xr = x + row * (long long)T;
+        float *yr = y + row * (long long)T;
+        if (vec) {
+            for (int c = threadIdx.x * 4; c < T; c += blockDim.x * 4) {
+                float4 a = ld_stream4(xr + c);
+                float r[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double p = (double)r[j] * taper_weight(c + j, T, htaper) * v;
+                    if (trunc_int) p = trunc(p);
+                    r[j] = (float)p;
+                }
+                st_stream4(yr + c, make_float4(r[0], r[1], r[2], r[3]));
+            }
+        } else {
+            for (int c = threadIdx.x; c < T; c += blockDim.x) {
+                double p = (double)xr[c] * taper_weight(c, T, htaper) * v;
+                if (trunc_int) p = trunc(p);
+                yr[c] = (float)p;
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------- hfilt
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+    typedef float4 type;
+    static constexpr int N = 4;
+};
+template <>
+struct Vec4<double> {
+    typedef double2 type;
+    static constexpr int N = 2;
+};
+
+__device__ __forceinline__ double block_sum(double v, double *red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();  // protect red[] from the previous use
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    double t = (lane < nw) ? red[lane] : 0.0;
+    t = warp_sum(t);
+    return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) hfilt_kernel(const T *__restrict__ x, T *__restrict__ y, int S, int Tn,
+                                                    long long rows, int htr1, int htrn,
+                                                    const double *__restrict__ taper, int trunc_avg) {
+    __shared__ double red[32];
+    constexpr int V = Vec4<T>::N;
+    typedef typename Vec4<T>::type VT;
+    const bool vec = ((Tn % V) == 0) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int s = (int)(row % S);
+        const T *xr = x + row * (long long)Tn;
+        T *yr = y + row * (long long)Tn;
+        // pass 1: sum over [htr1, htrn) - the row stays in L1/L2 for pass 2
+        double acc = 0.0;
+        if (vec) {
+            const int c0 = (htr1 / V) * V;
+            for (int c = c0 + threadIdx.x * V; c < htrn; c += blockDim.x * V) {
+                VT a = *reinterpret_cast<const VT *>(xr + c);
+                const T *e = reinterpret_cast<const T *>(&a);
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+                    if (c + j >= htr1 && c + j < htrn) acc += (double)e[j];
+            }
+        } else {
+            for (int c = htr1 + threadIdx.x; c < htrn; c += blockDim.x) acc += (double)xr[c];
+        }
+        const double total = block_sum(acc, red);
+        double avg = total / (double)(htrn - htr1) * taper[s];
+        if (trunc_avg) avg = trunc(avg);
+        const T avg_t = (T)avg;  // np.atleast_2d(avg_trace).transpose().astype(self.data.dtype)
+        if (vec) {
+            for (int c = threadIdx.x * V; c < Tn; c += blockDim.x * V) {
+                VT a = *reinterpret_cast<const VT *>(xr + c);
+                T *e = reinterpret_cast<T *>(&a);
+#pragma unroll
+                for (int j = 0; j < V; ++j) e[j] = e[j] - avg_t;
+                *reinterpret_cast<VT *>(yr + c) = a;
+            }
+        } else {
+            for (int c = threadIdx.x; c < Tn; c += blockDim.x) yr[c] = xr[c] - avg_t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- ahfilt
+// Column window of trace i (python slice semantics), _RadarDataFiltering.py:67-72.
+__device__ __forceinline__ void ahfilt_window(int i, int Tn, int w, int tail_lo, int &lo, int &hi) {
+    const int h = w / 2;
+    if (i <= h) {
+        lo = 0;
+        hi = min(h + i, Tn);
+    } else if (i >= Tn - h) {
+        lo = tail_lo;
+        hi = Tn;
+    } else {
+        lo = i - h + 1;
+        hi = i + h;
+    }
+    if (hi < lo) hi = lo;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ahfilt_kernel(const T *__restrict__ x, T *__restrict__ y, int S, int Tn,
+                                                     long long rows, int w, int tail_lo,
+                                                     const double *__restrict__ taper,
+                                                     double *__restrict__ gscratch) {
+    extern __shared__ double smem_d[];
+    __shared__ double warp_tot[8];
+    __shared__ double carry_s;
+    double *P = gscratch ? gscratch + (size_t)blockIdx.x * (size_t)(Tn + 1) : smem_d;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const long long b = row / S;
+        const int s = (int)(row % S);
+        const T *xb = x + b * (long long)S * Tn;
+        // the 7-tap triangular kernel on the odd-extended trace, folded onto real rows
+        int rrow[14];
+        double rcoef[14];
+        int nr = 0;
+#pragma unroll
+        for (int j = -3; j <= 3; ++j) {
+            const double c = (double)(4 - (j < 0 ? -j : j)) / 16.0;
+            const int n = s + j;
+            if (n < 0) {
+                rrow[nr] = 0; rcoef[nr++] = 2.0 * c;
+                rrow[nr] = -n; rcoef[nr++] = -c;
+            } else if (n >= S) {
+                rrow[nr] = S - 1; rcoef[nr++] = 2.0 * c;
+                rrow[nr] = 2 * (S - 1) - n; rcoef[nr++] = -c;
+            } else {
+                rrow[nr] = n; rcoef[nr++] = c;
+            }
+        }
+        if (threadIdx.x == 0) {
+            carry_s = 0.0;
+            P[0] = 0.0;
+        }
+        __syncthreads();
+        // inclusive prefix sum of f[c] = sum_j coef_j * x[row_j][c], chunk of 256 columns at a time
+        for (int c0 = 0; c0 < Tn; c0 += blockDim.x) {
+            const int c = c0 + threadIdx.x;
+            double f = 0.0;
+            if (c < Tn) {
+                for (int j = 0; j < nr; ++j) f += rcoef[j] * (double)xb[(long long)rrow[j] * Tn + c];
+            }
+            // warp inclusive scan
+            double v = f;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                double n = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += n;
+            }
+            if (lane == 31) warp_tot[warp] = v;
+            __syncthreads();
+            double off = carry_s;
+            for (int k = 0; k < warp; ++k) off += warp_tot[k];
+            if (c < Tn) P[c + 1] = v + off;
+            __syncthreads();
+            if (threadIdx.x == blockDim.x - 1) carry_s = v + off;
+            __syncthreads();
+        }
+        const double tp = taper[s];
+        const T *xr = xb + (long long)s * Tn;
+        T *yr = y + row * (long long)Tn;
+        for (int c = threadIdx.x; c < Tn; c += blockDim.x) {
+            int lo, hi;
+            ahfilt_window(c, Tn, w, tail_lo, lo, hi);
+            const double mean = (P[hi] - P[lo]) / (double)(hi - lo);  // 0/0 -> NaN like np.mean of empty
+            yr[c] = (T)((double)xr[c] - mean * tp);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ filtfilt
+struct IirCoef {
+    double b[33];
+    double a[33];
+    double zi[32];
+};
+
+template <typename T, int NS>
+__device__ __forceinline__ double iir_step(double xv, double (&z)[NS], const IirCoef &c) {
+    const double yv = fma(c.b[0], xv, z[0]);
+#pragma unroll
+    for (int i = 0; i < NS - 1; ++i) z[i] = fma(c.b[i + 1], xv, fma(-c.a[i + 1], yv, z[i + 1]));
+    z[NS - 1] = fma(c.b[NS], xv, -c.a[NS] * yv);
+    return yv;
+}
+
+template <typename T, int NS>
+__global__ void __launch_bounds__(64) filtfilt_kernel(const T *__restrict__ x, T *__restrict__ y,
+                                                      T *__restrict__ work, int S, int Tn, long long ntraces,
+                                                      int padlen, const __grid_constant__ IirCoef c) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= ntraces) return;
+    const long long b = gid / Tn;
+    const int t = (int)(gid % Tn);
+    const long long st = Tn;
+    const T *xb = x + b * (long long)S * Tn + t;
+    T *yb = y + b * (long long)S * Tn + t;
+    const int L = S + 2 * padlen;
+    T *wk = work + b * (long long)L * Tn + t;
+
+    const double x0 = (double)xb[0];
+    const double xl = (double)xb[(long long)(S - 1) * st];
+    double z[NS];
+    // ---- forward over the odd-extended trace
+    {
+        const double e0 = (padlen > 0) ? 2.0 * x0 - (double)xb[(long long)padlen * st] : x0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) z[i] = c.zi[i] * e0;
+    }
+    int k = 0;
+    for (; k < padlen; ++k) {
+        const double xv = 2.0 * x0 - (double)xb[(long long)(padlen - k) * st];
+        wk[(long long)k * st] = (T)iir_step<T, NS>(xv, z, c);
+    }
+    {
+        int i = 0;
+        for (; i + 8 <= S; i += 8) {
+            double xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = (double)xb[(long long)(i + u) * st];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) wk[(long long)(padlen + i + u) * st] = (T)iir_step<T, NS>(xv[u], z, c);
+        }
+        for (; i < S; ++i)
+            wk[(long long)(padlen + i) * st] = (T)iir_step<T, NS>((double)xb[(long long)i * st], z, c);
+    }
+    for (k = 0; k < padlen; ++k) {
+        const double xv = 2.0 * xl - (double)xb[(long long)(S - 2 - k) * st];
+        wk[(long long)(padlen + S + k) * st] = (T)iir_step<T, NS>(xv, z, c);
+    }
+    // ---- backward over the forward output
+    {
+        const double e0 = (double)wk[(long long)(L - 1) * st];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) z[i] = c.zi[i] * e0;
+    }
+    for (k = L - 1; k >= padlen + S; --k) (void)iir_step<T, NS>((double)wk[(long long)k * st], z, c);
+    {
+        int i = S - 1;
+        for (; i - 7 >= 0; i -= 8) {
+            double xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = (double)wk[(long long)(padlen + i - u) * st];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) yb[(long long)(i - u) * st] = (T)iir_step<T, NS>(xv[u], z, c);
+        }
+        for (; i >= 0; --i)
+            yb[(long long)i * st] = (T)iir_step<T, NS>((double)wk[(long long)(padlen + i) * st], z, c);
+    }
+}
+
+template <typename T, int NS>
+static int launch_filtfilt(const T *x, T *y, T *work, int S, int Tn, int batch, int padlen, const IirCoef &c,
+                           cudaStream_t st) {
+    const long long ntraces = (long long)batch * Tn;
+    const int block = 64;
+    const long long grid = (ntraces + block - 1) / block;
+    filtfilt_kernel<T, NS><<<(unsigned)grid, block, 0, st>>>(x, y, work, S, Tn, ntraces, padlen, c);
+    IMPDAR_LAUNCH_CHECK();
+    return IMPDAR_B200_OK;
+}
+
+template <typename T>
+static int filtfilt_impl(const T *x, T *y, int S, int Tn, int batch, const double *b, const double *a,
+                         int ncoef, const double *zi, int padlen, void *ws, size_t ws_bytes, void *stream) {
+    IMPDAR_CHECK_ARG(x && y && b && a && zi, "filtfilt: null pointer");
+    IMPDAR_CHECK_ARG(S > 0 && Tn > 0 && batch > 0, "filtfilt: bad shape");
+    IMPDAR_CHECK_ARG(ncoef >= 2 && ncoef <= 33, "filtfilt: ncoef must be in [2, 33], got %d", ncoef);
+    IMPDAR_CHECK_ARG(padlen >= 0 && S > padlen,
+                     "The length of the input vector x must be greater than padlen, which is %d.", padlen);
+    IMPDAR_CHECK_ARG(a[0] == 1.0, "filtfilt: coefficients must be normalised (a[0] == 1)");
+    const size_t need = impdar_filtfilt_workspace_bytes(S, Tn, batch, padlen, (int)sizeof(T));
+    IMPDAR_CHECK_ARG(ws && ws_bytes >= need, "filtfilt: workspace too small (%zu < %zu)", ws_bytes, need);
+    IirCoef c;
+    memset(&c, 0, sizeof(c));
+    for (int i = 0; i < ncoef; ++i) {
+        c.b[i] = b[i];
+        c.a[i] = a[i];
+    }
+    for (int i = 0; i < ncoef - 1; ++i) c.zi[i] = zi[i];
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ns = ncoef - 1;
+    T *work = (T *)ws;
+#define FF_CASE(N) \
+    if (ns <= N) return launch_filtfilt<T, N>(x, y, work, S, Tn, batch, padlen, c, st);
+    FF_CASE(2) FF_CASE(4) FF_CASE(6) FF_CASE(8) FF_CASE(10) FF_CASE(12) FF_CASE(16) FF_CASE(24) FF_CASE(32)
+#undef FF_CASE
+    set_error("filtfilt: unsupported order");
+    return IMPDAR_B200_EINVAL;
+}
+
+// ----------------------------------------------------------------------------------------------- FIR
+template <typename T>
+__global__ void __launch_bounds__(256) fir_kernel(const T *__restrict__ x, T *__restrict__ y, int S, int Tn,
+                                                  long long rows, const double *__restrict__ taps, int ntaps) {
+    extern __shared__ double tp[];
+    for (int i = threadIdx.x; i < ntaps; i += blockDim.x) tp[i] = taps[i];
+    __syncthreads();
+    const long long total = rows * (long long)Tn;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const long long row = g / Tn;
+        const int s = (int)(row % S);
+        const int kmax = min(ntaps - 1, s);
+        double acc = 0.0;
+        for (int k = 0; k <= kmax; ++k) acc = fma(tp[k], (double)x[g - (long long)k * Tn], acc);
+        y[g] = (T)acc;
+    }
+}
+
+template <typename T>
+static int fir_impl(const T *x, T *y, int S, int Tn, int batch, const double *taps, int ntaps, void *stream) {
+    IMPDAR_CHECK_ARG(x && y && taps, "fir: null pointer");
+    IMPDAR_CHECK_ARG(S > 0 && Tn > 0 && batch > 0, "fir: bad shape");
+    IMPDAR_CHECK_ARG(ntaps >= 1 && ntaps <= 1024, "fir: ntaps must be in [1, 1024]");
+    IMPDAR_CHECK_ARG(x != y, "fir: in-place not supported");
+    cudaStream_t st = (cudaStream_t)stream;
+    double *dtaps = nullptr;
+    IMPDAR_CUDA(cudaMallocAsync((void **)&dtaps, ntaps * sizeof(double), st));
+    IMPDAR_CUDA(cudaMemcpyAsync(dtaps, taps, ntaps * sizeof(double), cudaMemcpyHostToDevice, st));
+    const long long total = (long long)batch * S * Tn;
+    long long grid = (total + 255) / 256;
+    if (grid > (long long)num_sms() * 16) grid = (long long)num_sms() * 16;
+    fir_kernel<T><<<(unsigned)grid, 256, ntaps * sizeof(double), st>>>(x, y, S, Tn, (long long)batch * S, dtaps,
+                                                                      ntaps);
+    IMPDAR_LAUNCH_CHECK();
+    IMPDAR_CUDA(cudaFreeAsync(dtaps, st));
+    return IMPDAR_B200_OK;
+}
+
+template <typename T>
+static int hfilt_impl(const T *x, T *y, int S, int Tn, int batch, int htr1, int htrn, const double *taper,
+                      int trunc_avg, void *stream) {
+    IMPDAR_CHECK_ARG(x && y && taper, "hfilt: null pointer");
+    IMPDAR_CHECK_ARG(S > 0 && Tn > 0 && batch > 0, "hfilt: bad shape");
+    IMPDAR_CHECK_ARG(0 <= htr1 && htr1 < htrn && htrn <= Tn, "hfilt: bad trace bounds [%d, %d)", htr1, htrn);
+    const long long rows = (long long)batch * S;
+    long long grid = rows;
+    const long long cap = (long long)num_sms() * 32;
+    if (grid > cap) grid = cap;
+    hfilt_kernel<T><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, y, S, Tn, rows, htr1, htrn, taper,
+                                                                     trunc_avg);
+    IMPDAR_LAUNCH_CHECK();
+    return IMPDAR_B200_OK;
+}
+
+static const size_t AHFILT_SMEM_LIMIT = 200 * 1024;
+
+template <typename T>
+static int ahfilt_impl(const T *x, T *y, int S, int Tn, int batch, int w, const double *taper, void *ws,
+                       size_t ws_bytes, void *stream) {
+    IMPDAR_CHECK_ARG(x && y && taper, "ahfilt: null pointer");
+    IMPDAR_CHECK_ARG(S > 0 && Tn > 0 && batch > 0, "ahfilt: bad shape");
+    IMPDAR_CHECK_ARG(S > 12, "The length of the input vector x must be greater than padlen, which is 12.");
+    IMPDAR_CHECK_ARG(w >= 0, "ahfilt: window_size must be >= 0");
+    IMPDAR_CHECK_ARG((const void *)x != (const void *)y, "ahfilt: in-place not supported");
+    // python slice start of data[:, tnum - w : tnum]
+    int tail_lo = Tn - w;
+    if (tail_lo < 0) tail_lo = (tail_lo + Tn < 0) ? 0 : tail_lo + Tn;
+    const long long rows = (long long)batch * S;
+    const size_t need_smem = (size_t)(Tn + 1) * sizeof(double);
+    long long grid = rows;
+    double *scratch = nullptr;
+    size_t smem = need_smem;
+    if (need_smem > AHFILT_SMEM_LIMIT) {
+        const long long cap = (long long)num_sms() * 4;
+        if (grid > cap) grid = cap;
+        const size_t need = impdar_ahfilt_workspace_bytes(S, Tn, batch);
+        IMPDAR_CHECK_ARG(ws && ws_bytes >= need, "ahfilt: workspace too small (%zu < %zu)", ws_bytes, need);
+        scratch = (double *)ws;
+        smem = 0;
+    } else {
+        const long long cap = (long long)num_sms() * 16;
+        if (grid > cap) grid = cap;
+        if (smem > 48 * 1024)
+            IMPDAR_CUDA(cudaFuncSetAttribute(ahfilt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem));
+    }
+    ahfilt_kernel<T><<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(x, y, S, Tn, rows, w, tail_lo, taper,
+                                                                         scratch);
+    IMPDAR_LAUNCH_CHECK();
+    return IMPDAR_B200_OK;
+}
+
+}  // namespace impdar
+
+using namespace impdar;
+
+extern "C" {
+
+int impdar_taper_f32(const float *x, float *y, int S, int T, int batch, double htaper, double vtaper,
+                     int trunc_int, void *stream) {
+    IMPDAR_CHECK_ARG(x && y, "taper: null pointer");
+    IMPDAR_CHECK_ARG(S > 0 && T > 0 && batch > 0, "taper: bad shape");
+    const long long rows = (long long)batch * S;
+    long long grid = rows;
+    const long long cap = (long long)num_sms() * 32;
+    if (grid > cap) grid = cap;
+    taper_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, y, S, T, rows, htaper, vtaper, trunc_int);
+    IMPDAR_LAUNCH_CHECK();
+    return IMPDAR_B200_OK;
+}
+
+int impdar_hfilt_f32(const float *x, float *y, int S, int T, int batch, int htr1, int htrn,
+                     const double *taper, int trunc_avg, void *stream) {
+    return hfilt_impl<float>(x, y, S, T, batch, htr1, htrn, taper, trunc_avg, stream);
+}
+int impdar_hfilt_f64(const double *x, double *y, int S, int T, int batch, int htr1, int htrn,
+                     const double *taper, int trunc_avg, void *stream) {
+    return hfilt_impl<double>(x, y, S, T, batch, htr1, htrn, taper, trunc_avg, stream);
+}
+
+size_t impdar_ahfilt_workspace_bytes(int S, int T, int batch) {
+    (void)S;
+    (void)batch;
+    const size_t need_smem = (size_t)(T + 1) * sizeof(double);
+    if (need_smem <= AHFILT_SMEM_LIMIT) return 0;
+    return (size_t)num_sms() * 4 * (size_t)(T + 1) * sizeof(double);
+}
+int impdar_ahfilt_f32(const float *x, float *y, int S, int T, int batch, int w, const double *taper, void *ws,
+                      size_t ws_bytes, void *stream) {
+    return ahfilt_impl<float>(x, y, S, T, batch, w, taper, ws, ws_bytes, stream);
+}
+int impdar_ahfilt_f64(const double *x, double *y, int S, int T, int batch, int w, const double *taper, void *ws,
+                      size_t ws_bytes, void *stream) {
+    return ahfilt_impl<double>(x, y, S, T, batch, w, taper, ws, ws_bytes, stream);
+}
+
+size_t impdar_filtfilt_workspace_bytes(int S, int T, int batch, int padlen, int elem_bytes) {
+    return (size_t)batch * (size_t)(S + 2 * padlen) * (size_t)T * (size_t)elem_bytes;
+}
+int impdar_filtfilt_f32(const float *x, float *y, int S, int T, int batch, const double *b, const double *a,
+                        int ncoef, const double *zi, int padlen, void *ws, size_t ws_bytes, void *stream) {
+    return filtfilt_impl<float>(x, y, S, T, batch, b, a, ncoef, zi, padlen, ws, ws_bytes, stream);
+}
+int impdar_filtfilt_f64(const double *x, double *y, int S, int T, int batch, const double *b, const double *a,
+                        int ncoef, const double *zi, int padlen, void *ws, size_t ws_bytes, void *stream) {
+    return filtfilt_impl<double>(x, y, S, T, batch, b, a, ncoef, zi, padlen, ws, ws_bytes, stream);
+}
+int impdar_fir_f32(const float *x, float *y, int S, int T, int batch, const double *taps, int ntaps,
+                   void *stream) {
+    return fir_impl<float>(x, y, S, T, batch, taps, ntaps, stream);
+}
+int impdar_fir_f64(const double *x, double *y, int S, int T, int batch, const double *taps, int ntaps,
+                   void *stream) {
+    return fir_impl<double>(x, y, S, T, batch, taps, ntaps, stream);
+}
+
+}  // extern "C"

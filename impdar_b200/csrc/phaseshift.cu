@@ -1,0 +1,350 @@
+// Gazdag phase-shift migration, constant and layered velocity
+// (reference: migrationlib/mig_python.py:211-287 migrationPhaseShift, :361-493 phaseShift).
+//
+//   FK = fft2(taper(data), (nt, tnum)), nt = next pow2 >= snum
+//   const v : TK[tau,k] = 1/snum * sum_w [ (v kx/2)^2 < w^2 ] FK[w,k] * cp(w,k)^(tau+1),
+//             cp = exp(+i w dt sqrt(1 - (v kx/2)^2 / w^2))                                  (:403-420)
+//   v(tau)  : per tau, FK[w,k] *= exp(+i w dt Re sqrt(coss)), coss = 1 - (v_tau kx / 2w)^2;
+//             FK[w, coss <= thr2_tau] = 0 (sticky); TK[tau,k] = 1/snum * sum_w FK[w,k]      (:439-487)
+//   out = ifft_k(TK).real                                                                   (:282)
+//
+// Data are real, so FK(-w,-k) = conj FK(w,k) and TK(tau,-k) = conj TK(tau,k): only k = 0..tnum/2 is
+// computed (R2C along traces, C2C along time, C2R back), halving the work.
+//
+// The contraction over w is a per-kx non-uniform DFT (the "matrix" depends on kx), i.e. there is no
+// operand shared between columns, so it is kept as complex FMA on the SIMT pipes:
+//   * a CTA owns 2 kx columns and all nt frequencies; a thread keeps 16 (w,k) states in registers;
+//   * const v: the reference's own recurrence FFK *= cp, re-seeded every 64 steps from G = FK*cp^(64a)
+//     (G and cp^64 live in shared memory, both built from fp64 phases) so fp32 round-off cannot
+//     random-walk over thousands of steps;
+//   * layered: the cumulative phase is carried in fp64 turns (sqrt by fp32 rsqrt + one fp64 Newton step)
+//     and applied to the original FK with one fp32 sincos per (tau,w,k);
+//   * per-tau sums over w: in-thread, xor-shuffle, then one shared-memory pass per 64 taus.
+#include <cufft.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+extern "C" int impdar_taper_f32(const float *x, float *y, int S, int T, int batch, double htaper, double vtaper,
+                                int trunc_int, void *stream);
+
+namespace impdar {
+
+#define IMPDAR_CUFFT(call)                                                                  \
+    do {                                                                                    \
+        cufftResult r__ = (call);                                                           \
+        if (r__ != CUFFT_SUCCESS) {                                                         \
+            impdar::set_error("%s:%d %s -> cufft error %d", __FILE__, __LINE__, #call, (int)r__); \
+            return IMPDAR_B200_ECUFFT;                                                      \
+        }                                                                                   \
+    } while (0)
+
+constexpr int PS_THREADS = 512;
+constexpr int PS_TB = 64;  // taus per block (re-seed interval of the constant-velocity recurrence)
+
+struct PhshParams {
+    const float2 *FK;  // (nt, K)
+    float2 *TK;        // (S, K)
+    int nt, K, S, T;
+    double dt, dx, vel;
+    const double *vmig;  // S (layered) or null
+    const double *thr2;  // S (layered) or null
+    float inv_s;
+};
+
+__device__ __forceinline__ double ps_omega(int iw, int nt, double dt) {
+    // 2 pi fftfreq(nt, dt)[iw], with w == 0 replaced by 1e-10/dt (:404-406, :446-448)
+    const int fi = (iw < (nt + 1) / 2) ? iw : iw - nt;
+    if (fi == 0) return 1e-10 / dt;
+    return 2.0 * 3.14159265358979323846 * (double)fi / ((double)nt * dt);
+}
+__device__ __forceinline__ double ps_kx(int k, int T, double dx) {
+    return 2.0 * 3.14159265358979323846 * (double)k / ((double)T * dx);  // k <= T/2: the non-negative branch
+}
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// Sum `part` over the lanes that share a kx column and park the warp's result for tau slot b.
+template <int COLS>
+__device__ __forceinline__ void ps_park(float2 part, float2 (*buf)[PS_THREADS / 32][COLS], int b) {
+#pragma unroll
+    for (int o = COLS; o < 32; o <<= 1) {
+        part.x += __shfl_xor_sync(0xffffffffu, part.x, o);
+        part.y += __shfl_xor_sync(0xffffffffu, part.y, o);
+    }
+    const int lane = threadIdx.x & 31;
+    if (lane < COLS) buf[b][threadIdx.x >> 5][lane] = part;
+}
+
+// Sum the warps' parked partials of one tau block and store (or accumulate) TK.
+template <int COLS>
+__device__ __forceinline__ void ps_commit(const PhshParams &p, float2 (*buf)[PS_THREADS / 32][COLS], int tb0,
+                                          bool accumulate) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < PS_TB * COLS; i += PS_THREADS) {
+        const int b = i / COLS, c = i % COLS;
+        const int tau = tb0 + b, kk = blockIdx.x * COLS + c;
+        if (tau < p.S && kk < p.K) {
+            float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < PS_THREADS / 32; ++w) {
+                s.x += buf[b][w][c].x;
+                s.y += buf[b][w][c].y;
+            }
+            s.x *= p.inv_s;
+            s.y *= p.inv_s;
+            float2 *dst = p.TK + (size_t)tau * p.K + kk;
+            if (accumulate) {
+                const float2 o = *dst;
+                s.x += o.x;
+                s.y += o.y;
+            }
+            *dst = s;
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------ constant velocity (:396-420)
+constexpr int PSC_COLS = 2;
+constexpr int PSC_PER = 16;
+constexpr int PSC_WCHUNK = PS_THREADS / PSC_COLS * PSC_PER;  // 4096 frequencies per pass
+
+__global__ void __launch_bounds__(PS_THREADS, 1) phsh_const_kernel(const __grid_constant__ PhshParams p) {
+    extern __shared__ float2 ps_smem[];
+    float2 *G = ps_smem;                          // [PSC_PER][PS_THREADS]  FK * cp^(tb0)
+    float2 *Z64 = ps_smem + PSC_PER * PS_THREADS;  // [PSC_PER][PS_THREADS]  cp^64
+    __shared__ float2 buf[PS_TB][PS_THREADS / 32][PSC_COLS];
+
+    const int tid = threadIdx.x;
+    const int k = blockIdx.x * PSC_COLS + (tid % PSC_COLS);
+    const bool kvalid = k < p.K;
+    const double vk = p.vel * ps_kx(kvalid ? k : 0, p.T, p.dx) / 2.0;
+    const double vkx2 = vk * vk;  // (vmig*kx/2)^2   (:411)
+
+    for (int ch = 0; ch * PSC_WCHUNK < p.nt; ++ch) {
+        float2 z[PSC_PER];
+#pragma unroll
+        for (int i = 0; i < PSC_PER; ++i) {
+            const int iw = ch * PSC_WCHUNK + (tid / PSC_COLS) + i * (PS_THREADS / PSC_COLS);
+            float2 g = make_float2(0.f, 0.f), zz = make_float2(1.f, 0.f), z64 = zz;
+            if (kvalid && iw < p.nt) {
+                const double w = ps_omega(iw, p.nt, p.dt);
+                if (vkx2 < w * w) {  // propagating (:412)
+                    const double phi = w * p.dt * sqrt(1.0 - vkx2 / (w * w));  // = -phase (:415); cp = e^{+i phi}
+                    double sn, cs;
+                    sincos(phi, &sn, &cs);
+                    zz = make_float2((float)cs, (float)sn);
+                    sincos(phi * (double)PS_TB, &sn, &cs);
+                    z64 = make_float2((float)cs, (float)sn);
+                    g = p.FK[(size_t)iw * p.K + k];
+                }
+            }
+            z[i] = zz;
+            G[i * PS_THREADS + tid] = g;
+            Z64[i * PS_THREADS + tid] = z64;
+        }
+        for (int tb0 = 0; tb0 < p.S; tb0 += PS_TB) {
+            float2 ffk[PSC_PER];
+#pragma unroll
+            for (int i = 0; i < PSC_PER; ++i) ffk[i] = G[i * PS_THREADS + tid];
+            const int nb = min(PS_TB, p.S - tb0);
+            for (int b = 0; b < nb; ++b) {
+                float2 part = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < PSC_PER; ++i) {
+                    ffk[i] = cmulf(ffk[i], z[i]);  // FFK *= cp      (:419)
+                    part.x += ffk[i].x;            // TK[itau] += FFK (:420)
+                    part.y += ffk[i].y;
+                }
+                ps_park<PSC_COLS>(part, buf, b);
+            }
+#pragma unroll
+            for (int i = 0; i < PSC_PER; ++i)
+                G[i * PS_THREADS + tid] = cmulf(G[i * PS_THREADS + tid], Z64[i * PS_THREADS + tid]);
+            ps_commit<PSC_COLS>(p, buf, tb0, ch > 0);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------- layered v(tau) (:439-487)
+constexpr int PSL_PER = 8;
+constexpr int PSL_WCHUNK = PS_THREADS * PSL_PER;  // 4096 frequencies per pass, one kx column per CTA
+
+__global__ void __launch_bounds__(PS_THREADS, 1) phsh_layered_kernel(const __grid_constant__ PhshParams p) {
+    __shared__ float2 buf[PS_TB][PS_THREADS / 32][1];
+    const int tid = threadIdx.x;
+    const int k = blockIdx.x;
+    const double kx = ps_kx(k, p.T, p.dx);
+
+    for (int ch = 0; ch * PSL_WCHUNK < p.nt; ++ch) {
+        float2 fk0[PSL_PER];
+        double c[PSL_PER], wturn[PSL_PER], phase[PSL_PER];
+#pragma unroll
+        for (int i = 0; i < PSL_PER; ++i) {
+            const int iw = ch * PSL_WCHUNK + tid + i * PS_THREADS;
+            fk0[i] = make_float2(0.f, 0.f);
+            c[i] = 0.0;
+            wturn[i] = 0.0;
+            phase[i] = 0.0;
+            if (iw < p.nt) {
+                const double w = ps_omega(iw, p.nt, p.dt);
+                const double h = 0.5 * kx / w;
+                c[i] = h * h;                                        // coss = 1 - c * v^2   (:460)
+                wturn[i] = w * p.dt * 0.15915494309189535;           // phase advance in turns per unit sqrt(coss)
+                fk0[i] = p.FK[(size_t)iw * p.K + k];
+            }
+        }
+        for (int tb0 = 0; tb0 < p.S; tb0 += PS_TB) {
+            const int nb = min(PS_TB, p.S - tb0);
+            for (int b = 0; b < nb; ++b) {
+                const double v = p.vmig[tb0 + b];
+                const double v2 = v * v;
+                const double th = p.thr2[tb0 + b];
+                float2 part = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < PSL_PER; ++i) {
+                    const double coss = fma(-c[i], v2, 1.0);
+                    if (coss <= th) {  // evanescent from here on (:484-485, sticky because FK itself is zeroed)
+                        fk0[i] = make_float2(0.f, 0.f);
+                    } else {
+                        // sqrt(coss): fp32 rsqrt seed + one fp64 Newton step (error ~1e-14)
+                        const float cf = (float)coss;
+                        float rs;
+                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(cf));
+                        const double s0 = (double)(cf * rs);
+                        const double s1 = fma(fma(-s0, s0, coss), (double)(0.5f * rs), s0);
+                        phase[i] = fma(wturn[i], s1, phase[i]);
+                        const double fr = phase[i] - rint(phase[i]);
+                        float sn, cs;
+                        __sincosf((float)fr * 6.283185307179586f, &sn, &cs);
+                        part.x += fmaf(fk0[i].x, cs, -fk0[i].y * sn);
+                        part.y += fmaf(fk0[i].x, sn, fk0[i].y * cs);
+                    }
+                }
+                ps_park<1>(part, buf, b);
+            }
+            ps_commit<1>(p, buf, tb0, ch > 0);
+        }
+    }
+}
+
+struct PhshPlans {
+    cufftHandle r2c = 0, c2c = 0, c2r = 0;
+};
+static std::map<std::tuple<int, int, int, int>, PhshPlans> g_ps_plans;  // (device, S, T, nt)
+static std::mutex g_ps_mu;
+
+static int ps_get_plans(int S, int T, int nt, PhshPlans &out) {
+    int dev = 0;
+    IMPDAR_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_ps_mu);
+    auto key = std::make_tuple(dev, S, T, nt);
+    auto it = g_ps_plans.find(key);
+    if (it != g_ps_plans.end()) {
+        out = it->second;
+        return IMPDAR_B200_OK;
+    }
+    const int K = T / 2 + 1;
+    PhshPlans pl;
+    {
+        int n[1] = {T};
+        IMPDAR_CUFFT(cufftPlanMany(&pl.r2c, 1, n, nullptr, 1, T, nullptr, 1, K, CUFFT_R2C, S));
+    }
+    {
+        int n[1] = {nt}, emb[1] = {nt};
+        IMPDAR_CUFFT(cufftPlanMany(&pl.c2c, 1, n, emb, K, 1, emb, K, 1, CUFFT_C2C, K));
+    }
+    {
+        int n[1] = {T};
+        IMPDAR_CUFFT(cufftPlanMany(&pl.c2r, 1, n, nullptr, 1, K, nullptr, 1, T, CUFFT_C2R, S));
+    }
+    g_ps_plans[key] = pl;
+    out = pl;
+    return IMPDAR_B200_OK;
+}
+
+static inline int ps_next_pow2(int S) {
+    int nt = 1;
+    while (nt < S) nt <<= 1;
+    return nt;
+}
+
+__global__ void scale_kernel(float *x, size_t n, float s) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        x[i] *= s;
+}
+
+}  // namespace impdar
+
+using namespace impdar;
+
+extern "C" {
+
+size_t impdar_phsh_workspace_bytes(int S, int T) {
+    const size_t nt = (size_t)ps_next_pow2(S);
+    const size_t K = (size_t)(T / 2 + 1);
+    const size_t fk = nt * K * sizeof(float2);
+    const size_t tk = (size_t)S * K * sizeof(float2);
+    const size_t real = (size_t)S * (size_t)T * sizeof(float);
+    return fk + (tk > real ? tk : real) + 2048;
+}
+
+int impdar_phsh_f32(const float *data, float *out, int S, int T, double dt, double dx, double vel,
+                    const double *vmig, const double *thr2, double htaper, double vtaper, void *workspace,
+                    size_t ws_bytes, void *stream) {
+    IMPDAR_CHECK_ARG(data && out, "phsh: null pointer");
+    IMPDAR_CHECK_ARG(S >= 1 && T >= 1, "phsh: bad shape");
+    IMPDAR_CHECK_ARG(dt > 0.0 && dx != 0.0, "phsh: dt must be positive and dx non-zero");
+    IMPDAR_CHECK_ARG((vmig == nullptr) == (thr2 == nullptr), "phsh: vmig and thr2 go together");
+    const size_t need = impdar_phsh_workspace_bytes(S, T);
+    IMPDAR_CHECK_ARG(workspace && ws_bytes >= need, "phsh: workspace too small (%zu < %zu)", ws_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = ps_next_pow2(S);
+    const int K = T / 2 + 1;
+    const size_t fk_bytes = (size_t)nt * K * sizeof(float2);
+    char *w = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    float2 *FK = (float2 *)w;
+    char *w2 = w + ((fk_bytes + 255) & ~(size_t)255);
+    float *tap = (float *)w2;    // tapered data, dead once the R2C has run
+    float2 *TK = (float2 *)w2;   // ... so TK may overlay it
+
+    PhshPlans pl;
+    int rc = ps_get_plans(S, T, nt, pl);
+    if (rc) return rc;
+    IMPDAR_CUFFT(cufftSetStream(pl.r2c, st));
+    IMPDAR_CUFFT(cufftSetStream(pl.c2c, st));
+    IMPDAR_CUFFT(cufftSetStream(pl.c2r, st));
+
+    rc = impdar_taper_f32(data, tap, S, T, 1, htaper, vtaper, 0, stream);
+    if (rc) return rc;
+    if (nt > S) IMPDAR_CUDA(cudaMemsetAsync(FK + (size_t)S * K, 0, (size_t)(nt - S) * K * sizeof(float2), st));
+    IMPDAR_CUFFT(cufftExecR2C(pl.r2c, tap, (cufftComplex *)FK));                                   // x -> kx
+    IMPDAR_CUFFT(cufftExecC2C(pl.c2c, (cufftComplex *)FK, (cufftComplex *)FK, CUFFT_FORWARD));     // t -> w
+    count_launch(2);
+
+    PhshParams p;
+    p.FK = FK; p.TK = TK; p.nt = nt; p.K = K; p.S = S; p.T = T;
+    p.dt = dt; p.dx = fabs(dx); p.vel = vel; p.vmig = vmig; p.thr2 = thr2;
+    p.inv_s = (float)(1.0 / (double)S);
+    if (vmig == nullptr) {
+        const size_t smem = 2 * (size_t)PSC_PER * PS_THREADS * sizeof(float2);
+        IMPDAR_CUDA(cudaFuncSetAttribute(phsh_const_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        phsh_const_kernel<<<(K + PSC_COLS - 1) / PSC_COLS, PS_THREADS, smem, st>>>(p);
+    } else {
+        phsh_layered_kernel<<<K, PS_THREADS, 0, st>>>(p);
+    }
+    IMPDAR_LAUNCH_CHECK();
+    IMPDAR_CUFFT(cufftExecC2R(pl.c2r, (cufftComplex *)TK, out));  // kx -> x (unnormalised)
+    count_launch(1);
+    const size_t n = (size_t)S * T;
+    scale_kernel<<<num_sms() * 8, 256, 0, st>>>(out, n, (float)(1.0 / (double)T));  // numpy ifft's 1/T
+    IMPDAR_LAUNCH_CHECK();
+    return IMPDAR_B200_OK;
+}
+
+}  // extern "C"

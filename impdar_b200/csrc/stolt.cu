@@ -1,0 +1,183 @@
+// Stolt f-k migration (reference: migrationlib/mig_python.py:126-208).
+//
+//   taper -> rfft2(axes=(1,0)) -> for every (kz_j, kx): KK = lin-interp_w FK[:, kx] at w' = sqrt(w_j^2 + (v kx/2)^2)
+//   (clamped to the Nyquist row, FITPACK k=1 semantics) * w_j/w' -> KK[0,0] = 0 -> irfft2(axes=(1,0)).
+//
+// Device pipeline per profile (HBM-bound, five sweeps):
+//   1 taper (fp32, vectorised)            2 cuFFT R2C along time (stride = tnum, batch = tnum)
+//   3 cuFFT C2C along traces, in place    4 remap + obliquity + 1/(S'T) scale kernel (this file)
+//   5 cuFFT C2C inverse along traces      6 cuFFT C2R along time
+// The remap coordinate f = w'/dw = sqrt(j^2 + beta^2) is evaluated in fp64 (f reaches ~snum/2 and the
+// interpolation weight is its fractional part); the interpolation itself is fp32 complex FMA.
+#include <cufft.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+extern "C" int impdar_taper_f32(const float *x, float *y, int S, int T, int batch, double htaper, double vtaper,
+                                int trunc_int, void *stream);
+
+namespace impdar {
+
+#define IMPDAR_CUFFT(call)                                                                  \
+    do {                                                                                    \
+        cufftResult r__ = (call);                                                           \
+        if (r__ != CUFFT_SUCCESS) {                                                         \
+            impdar::set_error("%s:%d %s -> cufft error %d", __FILE__, __LINE__, #call, (int)r__); \
+            return IMPDAR_B200_ECUFFT;                                                      \
+        }                                                                                   \
+    } while (0)
+
+struct StoltRemapParams {
+    const float2 *FK;  // (M, T)
+    float2 *KK;        // (M, T)
+    int M, T, nz;
+    double beta_unit;  // beta = beta_unit * kxi   (kxi = signed fft index of the column)
+    float norm;        // 1 / (S' * T)
+};
+
+__global__ void __launch_bounds__(128) stolt_remap_kernel(const __grid_constant__ StoltRemapParams p, int rows_per_cta) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= p.T) return;
+    const int kxi = (x <= (p.T - 1) / 2) ? x : x - p.T;  // np.fft.fftfreq ordering
+    const double beta = p.beta_unit * (double)kxi;
+    const double beta2 = beta * beta;
+    const int j0 = blockIdx.y * rows_per_cta;
+    const int j1 = min(p.M, j0 + rows_per_cta);
+    const double fmax = (double)(p.M - 1);
+    int cur = -2;
+    float2 v0 = make_float2(0.f, 0.f), v1 = v0;
+    for (int j = j0; j < j1; ++j) {
+        float2 o = make_float2(0.f, 0.f);
+        if (j < p.nz && p.M > 1) {
+            const double f = sqrt((double)j * (double)j + beta2);
+            const double fq = fmin(f, fmax);
+            int i0 = (int)fq;
+            i0 = min(i0, p.M - 2);
+            const float a = (float)(fq - (double)i0);
+            if (i0 != cur) {
+                if (i0 == cur + 1) {
+                    v0 = v1;
+                } else {
+                    v0 = p.FK[(size_t)i0 * p.T + x];
+                }
+                v1 = p.FK[(size_t)(i0 + 1) * p.T + x];
+                cur = i0;
+            }
+            // scaling = kZ / sqrt(kX^2 + kZ^2) = j / f ; (0,0) is 0/0 in the reference and then set to 0
+            const float sc = (f > 0.0) ? (float)((double)j / f) * p.norm : 0.f;
+            const float w0 = (1.f - a) * sc, w1 = a * sc;
+            o.x = fmaf(v0.x, w0, v1.x * w1);
+            o.y = fmaf(v0.y, w0, v1.y * w1);
+        }
+        p.KK[(size_t)j * p.T + x] = o;
+    }
+}
+
+struct StoltPlans {
+    cufftHandle r2c = 0, c2c = 0, c2r = 0;
+};
+static std::map<std::tuple<int, int, int>, StoltPlans> g_plans;  // (device, S, T)
+static std::mutex g_plans_mu;
+
+static int get_plans(int S, int T, StoltPlans &out) {
+    int dev = 0;
+    IMPDAR_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_plans_mu);
+    auto key = std::make_tuple(dev, S, T);
+    auto it = g_plans.find(key);
+    if (it != g_plans.end()) {
+        out = it->second;
+        return IMPDAR_B200_OK;
+    }
+    StoltPlans pl;
+    const int M = S / 2 + 1;
+    const int S2 = 2 * (M - 1);
+    {
+        int n[1] = {S}, inembed[1] = {S}, onembed[1] = {M};
+        IMPDAR_CUFFT(cufftPlanMany(&pl.r2c, 1, n, inembed, T, 1, onembed, T, 1, CUFFT_R2C, T));
+    }
+    {
+        int n[1] = {T};
+        IMPDAR_CUFFT(cufftPlanMany(&pl.c2c, 1, n, nullptr, 1, T, nullptr, 1, T, CUFFT_C2C, M));
+    }
+    if (S2 >= 1) {
+        int n[1] = {S2}, inembed[1] = {M}, onembed[1] = {S2};
+        IMPDAR_CUFFT(cufftPlanMany(&pl.c2r, 1, n, inembed, T, 1, onembed, T, 1, CUFFT_C2R, T));
+    }
+    g_plans[key] = pl;
+    out = pl;
+    return IMPDAR_B200_OK;
+}
+
+}  // namespace impdar
+
+using namespace impdar;
+
+extern "C" {
+
+size_t impdar_stolt_workspace_bytes(int S, int T, int batch) {
+    (void)batch;  // profiles are processed one at a time through the same buffers
+    const size_t M = (size_t)(S / 2 + 1);
+    const size_t cplx = M * (size_t)T * sizeof(float2);
+    const size_t real = (size_t)S * (size_t)T * sizeof(float);
+    const size_t a = cplx > real ? cplx : real;
+    return a + cplx + 1024;
+}
+
+int impdar_stolt_f32(const float *data, float *out, int S, int T, int batch, double dt, double dx, double vel,
+                     double htaper, double vtaper, int trunc_int, void *workspace, size_t ws_bytes,
+                     void *stream) {
+    IMPDAR_CHECK_ARG(data && out, "stolt: null pointer");
+    IMPDAR_CHECK_ARG(S >= 2 && T >= 1 && batch >= 1, "stolt: need snum >= 2, tnum >= 1, batch >= 1");
+    IMPDAR_CHECK_ARG(dt > 0.0 && vel > 0.0 && dx != 0.0, "stolt: dt, vel must be positive and dx non-zero");
+    const size_t need = impdar_stolt_workspace_bytes(S, T, batch);
+    IMPDAR_CHECK_ARG(workspace && ws_bytes >= need, "stolt: workspace too small (%zu < %zu)", ws_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = S / 2 + 1;
+    const int S2 = 2 * (M - 1);
+    const size_t cplx = (size_t)M * T * sizeof(float2);
+    const size_t real = (size_t)S * T * sizeof(float);
+    char *w = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    float *bufA = (float *)w;              // tapered input, later the remapped spectrum KK
+    float2 *bufKK = (float2 *)w;
+    float2 *bufFK = (float2 *)(w + (((cplx > real ? cplx : real) + 255) & ~(size_t)255));
+
+    StoltPlans pl;
+    int rc = get_plans(S, T, pl);
+    if (rc) return rc;
+    IMPDAR_CUFFT(cufftSetStream(pl.r2c, st));
+    IMPDAR_CUFFT(cufftSetStream(pl.c2c, st));
+    IMPDAR_CUFFT(cufftSetStream(pl.c2r, st));
+
+    StoltRemapParams rp;
+    rp.M = M; rp.T = T; rp.nz = S / 2;
+    // beta = (vel * kx / 2) / dw,  kx = 2 pi kxi / (T dx),  dw = 2 pi / (S dt)
+    rp.beta_unit = vel * (double)S * dt / (2.0 * (double)T * dx);
+    rp.norm = (float)(1.0 / ((double)S2 * (double)T));
+
+    for (int b = 0; b < batch; ++b) {
+        const float *din = data + (size_t)b * S * T;
+        float *dout = out + (size_t)b * S2 * T;
+        rc = impdar_taper_f32(din, bufA, S, T, 1, htaper, vtaper, trunc_int, stream);
+        if (rc) return rc;
+        IMPDAR_CUFFT(cufftExecR2C(pl.r2c, bufA, (cufftComplex *)bufFK));
+        IMPDAR_CUFFT(cufftExecC2C(pl.c2c, (cufftComplex *)bufFK, (cufftComplex *)bufFK, CUFFT_FORWARD));
+        count_launch(2);
+        rp.FK = bufFK;
+        rp.KK = bufKK;
+        const int rows_per_cta = 32;
+        dim3 grid((T + 127) / 128, (M + rows_per_cta - 1) / rows_per_cta);
+        stolt_remap_kernel<<<grid, 128, 0, st>>>(rp, rows_per_cta);
+        IMPDAR_LAUNCH_CHECK();
+        IMPDAR_CUFFT(cufftExecC2C(pl.c2c, (cufftComplex *)bufKK, (cufftComplex *)bufKK, CUFFT_INVERSE));
+        IMPDAR_CUFFT(cufftExecC2R(pl.c2r, (cufftComplex *)bufKK, dout));
+        count_launch(2);
+    }
+    return IMPDAR_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+"""A minimal host-side radargram object with the attributes the hot path touches
+(RadarData/__init__.py:132-204: data, snum, tnum, dt, travel_time [us], dist [km], trace_int [m], flags)
+and the hot-path methods bound to the B200 backend.  It exists so the backend can be used and tested
+where ImpDAR itself is not installed (the GPU box); with ImpDAR present, ``impdar_b200.install()`` binds
+the same functions onto ImpDAR's own RadarData instead.
+"""
+import numpy as np
+
+from . import filtering
+
+
+class RadarFlags(object):
+    """The processing-history flags the hot path sets (RadarFlags.py:44-61)."""
+
+    def __init__(self):
+        self.batch = False
+        self.bpass = np.zeros((3,))
+        self.hfilt = np.zeros((2,))
+        self.rgain = False
+        self.agc = False
+        self.restack = False
+        self.reverse = False
+        self.crop = np.zeros((3,))
+        self.nmo = np.zeros((2,))
+        self.interp = np.zeros((2,))
+        self.mig = 'none'
+        self.elev = 0
+        self.elevation = 0
+
+
+class RadarData(object):
+    """Radargram + geometry.  ``data`` is (snum, tnum), C-order, traces contiguous."""
+
+    def __init__(self, data=None, dt=None, travel_time=None, dist=None, trace_int=None):
+        self.data = data
+        self.snum = None if data is None else int(data.shape[0])
+        self.tnum = None if data is None else int(data.shape[1])
+        self.dt = dt
+        self.travel_time = travel_time
+        self.dist = dist
+        self.trace_int = trace_int
+        self.flags = RadarFlags()
+        self.fn = None
+
+    adaptivehfilt = filtering.adaptivehfilt
+    horizontalfilt = filtering.horizontalfilt
+    hfilt = filtering.hfilt
+    vertical_band_pass = filtering.vertical_band_pass
+    migrate = filtering.migrate

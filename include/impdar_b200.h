@@ -1,0 +1,137 @@
+/*
+ * impdar_b200.h - C ABI of libimpdar_b200.so: the B200 (sm_100a) backend for ImpDAR's radargram
+ * migration + filtering hot path.
+ *
+ * Reference interfaces replaced (paths relative to the reference's src/impdar/lib/):
+ *   - migrationlib/mig_cython.h:11            void mig_kirch_loop(...)     the one C-ABI precedent
+ *   - migrationlib/mig_python.py:35-123       migrationKirchhoff[Loop]
+ *   - migrationlib/mig_python.py:126-208      migrationStolt
+ *   - migrationlib/mig_python.py:211-287,361-493  migrationPhaseShift / phaseShift (const, layered)
+ *   - migrationlib/mig_python.py:290-355      migrationTimeWavenumber (taper-only stub)
+ *   - RadarData/_RadarDataFiltering.py:469-549  vertical_band_pass  (filtfilt / FIR lfilter)
+ *   - RadarData/_RadarDataFiltering.py:93-135   horizontalfilt
+ *   - RadarData/_RadarDataFiltering.py:19-90    adaptivehfilt
+ *
+ * Conventions
+ *   - A radargram is a C-order (snum, tnum) array: row = time sample, column = trace, traces contiguous
+ *     (RadarData/__init__.py:136-137).  `batch` profiles are stacked (batch, snum, tnum).
+ *   - Unless a parameter is documented as HOST, pointers are DEVICE pointers on the current CUDA device.
+ *     Small coefficient vectors (filter taps, states) are HOST pointers and are copied at launch.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls enqueue work and return; they never synchronise
+ *     (except the *_host entry points, which own their transfers and return finished results).
+ *   - Return value: 0 ok; 1 bad argument; 2 CUDA error; 3 cuFFT error.  impdar_b200_last_error() gives
+ *     the message of the last failure on the calling thread.
+ *   - No torch types, no C++ types: plain pointers and sizes.
+ */
+#ifndef IMPDAR_B200_H
+#define IMPDAR_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMPDAR_B200_OK 0
+#define IMPDAR_B200_EINVAL 1
+#define IMPDAR_B200_ECUDA 2
+#define IMPDAR_B200_ECUFFT 3
+
+int impdar_b200_version(void);
+const char *impdar_b200_last_error(void);
+/* Number of kernels launched by this library on the calling process since load (bench `gpu_launches`). */
+unsigned long long impdar_b200_launch_count(void);
+
+/* ---------------------------------------------------------------- taper (mig_python.py:152-157) --- */
+/* y = x * h[t] * v[s],  h = min(min(t, T-1-t)/htaper, 1), v likewise.  trunc_int != 0 reproduces the
+ * reference's cast back to an integer input dtype (truncation toward zero).  x == y allowed.          */
+int impdar_taper_f32(const float *x, float *y, int snum, int tnum, int batch, double htaper,
+                     double vtaper, int trunc_int, void *stream);
+
+/* ----------------------------------------------- horizontalfilt (_RadarDataFiltering.py:93-135) --- */
+/* y[s,t] = x[s,t] - (T)(mean(x[s, htr1:htrn]) * taper[s]);  taper: device, snum doubles.
+ * trunc_avg != 0 truncates the scaled mean toward zero first (integer input dtype).                   */
+int impdar_hfilt_f32(const float *x, float *y, int snum, int tnum, int batch, int htr1, int htrn,
+                     const double *taper, int trunc_avg, void *stream);
+int impdar_hfilt_f64(const double *x, double *y, int snum, int tnum, int batch, int htr1, int htrn,
+                     const double *taper, int trunc_avg, void *stream);
+
+/* ------------------------------------------------ adaptivehfilt (_RadarDataFiltering.py:19-90) --- */
+/* Per trace i the mean over the reference's column window, the 7-tap triangular time filter that
+ * filtfilt([.25]*4, 1, .) amounts to on the odd-extended mean trace, the exp taper, the subtraction.
+ * Requires snum > 12 (scipy's padlen).  workspace: impdar_ahfilt_workspace_bytes() bytes (may be 0). */
+size_t impdar_ahfilt_workspace_bytes(int snum, int tnum, int batch);
+int impdar_ahfilt_f32(const float *x, float *y, int snum, int tnum, int batch, int window_size,
+                      const double *taper, void *workspace, size_t workspace_bytes, void *stream);
+int impdar_ahfilt_f64(const double *x, double *y, int snum, int tnum, int batch, int window_size,
+                      const double *taper, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------- vertical_band_pass (_RadarDataFiltering.py:469-549): filtfilt --- */
+/* scipy.signal.filtfilt(b, a, x, axis=0), padtype 'odd': transposed direct-form-II in fp64 state, one
+ * trace per thread.  b, a, zi: HOST pointers; b and a have ncoef entries (normalised so a[0] == 1,
+ * zero-padded to a common length), zi has ncoef-1 entries (scipy.signal.lfilter_zi).
+ * 2 <= ncoef <= 33, snum > padlen.  workspace holds the forward pass over the padded trace.           */
+size_t impdar_filtfilt_workspace_bytes(int snum, int tnum, int batch, int padlen, int elem_bytes);
+int impdar_filtfilt_f32(const float *x, float *y, int snum, int tnum, int batch, const double *b,
+                        const double *a, int ncoef, const double *zi, int padlen, void *workspace,
+                        size_t workspace_bytes, void *stream);
+int impdar_filtfilt_f64(const double *x, double *y, int snum, int tnum, int batch, const double *b,
+                        const double *a, int ncoef, const double *zi, int padlen, void *workspace,
+                        size_t workspace_bytes, void *stream);
+/* y = scipy.signal.lfilter(taps, 1, x, axis=0) (the 'fir' branch, :536-540).  taps: HOST, ntaps<=1024 */
+int impdar_fir_f32(const float *x, float *y, int snum, int tnum, int batch, const double *taps,
+                   int ntaps, void *stream);
+int impdar_fir_f64(const double *x, double *y, int snum, int tnum, int batch, const double *taps,
+                   int ntaps, void *stream);
+
+/* ------------------------------------------------------ Kirchhoff (mig_python.py:35-123) --- */
+/* out[:, x - x_begin] for output traces x in [x_begin, x_end) of the (snum, tnum) radargram `data`
+ * (the whole input is needed: the aperture is only limited by 2r/v <= max(tt)).
+ *   dist_m : HOST, tnum doubles, trace positions in metres (dat.dist * 1e3, mig_python.py:108)
+ *   tt_s   : HOST, snum doubles, two-way travel time in seconds (strictly ascending)
+ *   grad_coef : HOST, 3*snum doubles: rows a, b, c of np.gradient's stencil g[s] = a f[s-1] + b f[s] + c f[s+1]
+ *            (b == 0 everywhere selects numpy's uniform-spacing branch; see impdar_b200/migrationlib.py)
+ *   out    : (snum, x_end - x_begin) floats
+ * The nearest-sample pick and the 2r/v > max(tt) cut are evaluated with the reference's float64
+ * operation sequence wherever float32 could decide differently, so the chosen samples are identical. */
+size_t impdar_kirchhoff_workspace_bytes(int snum, int tnum, int nearfield);
+int impdar_kirchhoff_f32(const float *data, float *out, int snum, int tnum, const double *dist_m,
+                         const double *tt_s, const double *grad_coef, double vel, int nearfield,
+                         int x_begin, int x_end, void *workspace, size_t workspace_bytes, void *stream);
+/* Counters of the last impdar_kirchhoff_f32 call (for the roofline): (output sample, input trace) pairs
+ * inside the aperture and pairs that took the float64 exact path.  Counting pairs costs an instruction
+ * per pair, so it is off unless enabled.  last_stats synchronises the stream of that call.            */
+int impdar_kirchhoff_enable_stats(int on);
+int impdar_kirchhoff_last_stats(unsigned long long *pairs, unsigned long long *exact_pairs);
+
+/* Reference prototype, migrationlib/mig_cython.h:11 - HOST pointers, float64, synchronous.  Linking
+ * the reference's own Cython shim (_mig_cython.pyx) against libimpdar_b200.so resolves this symbol.
+ * nearfield != 0 needs the un-differentiated data, which this prototype does not carry: the call then
+ * fills migdata with NaN and records an error (use impdar_kirchhoff_host_f64 instead).                */
+void mig_kirch_loop(double *migdata, int tnum, int snum, double *dist, double *zs, double *zs2,
+                    double *tt_sec, double vel, double *gradD, double max_travel_time, int nearfield);
+/* Same, with the data pointer and a status: HOST float64 in/out (the drop-in for migrationKirchhoff). */
+int impdar_kirchhoff_host_f64(const double *data, double *migdata, int snum, int tnum,
+                              const double *dist_m, const double *tt_s, double vel, int nearfield);
+
+/* ---------------------------------------------------------- Stolt (mig_python.py:126-208) --- */
+/* data (batch, snum, tnum) -> out (batch, 2*(snum/2), tnum).  dx = mean trace spacing [m] (:163-168). */
+size_t impdar_stolt_workspace_bytes(int snum, int tnum, int batch);
+int impdar_stolt_f32(const float *data, float *out, int snum, int tnum, int batch, double dt, double dx,
+                     double vel, double htaper, double vtaper, int trunc_int, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* -------------------------------------- phase shift (mig_python.py:211-287, 361-493) --- */
+/* data (snum, tnum) -> out (snum, tnum).  vmig == NULL: constant velocity `vel` (:396-420);
+ * otherwise vmig: device, snum doubles, the layered profile from getVelocityProfile (:439-487) and
+ * thr2: device, snum doubles, the per-tau evanescent threshold (tau/travel_time[-1]/1e6)^2 (:484).
+ * tt0 is unused by the reference arithmetic and therefore absent.                                      */
+size_t impdar_phsh_workspace_bytes(int snum, int tnum);
+int impdar_phsh_f32(const float *data, float *out, int snum, int tnum, double dt, double dx, double vel,
+                    const double *vmig, const double *thr2, double htaper, double vtaper,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMPDAR_B200_H */

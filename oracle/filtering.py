@@ -1,0 +1,161 @@
+"""CPU oracle for the filtering hot path: float64 numpy/scipy restatement of
+RadarData/_RadarDataFiltering.py (vertical_band_pass, horizontalfilt, adaptivehfilt).
+
+TEST INFRASTRUCTURE ONLY (see oracle/migration.py header).  Parity is PINNED against the running
+reference (tests/test_oracle_vs_reference.py) and against tests/golden/*.npz generated from it,
+including the reference's exact known-answer fixture ``hfilt_target_output``
+(NoInitRadarData.py:74-76, test_RadarDataFiltering.py:53-57).
+"""
+import numpy as np
+
+
+def exp_taper(travel_time_us):
+    """exp(-0.05 tt)/exp(-0.05 tt[0]), _RadarDataFiltering.py:59 and :129-130."""
+    tt = np.asarray(travel_time_us, dtype=np.float64).flatten()
+    return np.exp(-tt * 0.05) / np.exp(-tt[0] * 0.05)
+
+
+def hfilt_bounds(ntr1, ntr2, tnum):
+    """_RadarDataFiltering.py:122-123."""
+    htr1 = int(max(0, min(ntr1, tnum - 1)))
+    htrn = int(max(htr1 + 1, min(ntr2, tnum)))
+    return htr1, htrn
+
+
+def horizontalfilt(data, travel_time_us, ntr1, ntr2):
+    """_RadarDataFiltering.py:93-135."""
+    data = np.asarray(data)
+    htr1, htrn = hfilt_bounds(ntr1, ntr2, data.shape[1])
+    avg_trace = np.mean(data[:, htr1:htrn], axis=-1)
+    avg_trace = avg_trace * exp_taper(travel_time_us)
+    return data - np.atleast_2d(avg_trace).transpose().astype(data.dtype)
+
+
+def adaptive_window(i, tnum, window_size):
+    """Column window [lo, hi) of trace i, _RadarDataFiltering.py:67-72, with Python's slice rules
+    (negative start wraps once, bounds clip)."""
+    h = window_size // 2
+    if i <= h:
+        sl = slice(0, h + i)
+    elif i >= tnum - h:
+        sl = slice(int(tnum) - window_size, int(tnum))
+    else:
+        sl = slice(i - h + 1, i + h)
+    lo, hi, _ = sl.indices(tnum)
+    return lo, max(lo, hi)
+
+
+def adaptivehfilt_loops(data, travel_time_us, window_size):
+    """Same loop as the reference (_RadarDataFiltering.py:65-85): per trace re-mean + scipy filtfilt."""
+    from scipy.signal import filtfilt
+    data = np.asarray(data)
+    S, T = data.shape
+    scale = exp_taper(travel_time_us)
+    out = np.zeros_like(data, dtype=data.dtype)
+    for i in range(int(T)):
+        if i <= window_size // 2:
+            pk = data[:, 0:window_size // 2 + i].copy()
+        elif i >= T - window_size // 2:
+            pk = data[:, int(T) - window_size:int(T)].copy()
+        else:
+            pk = data[:, i - window_size // 2 + 1:i + window_size // 2].copy()
+        low = filtfilt([.25, .25, .25, .25], 1, np.mean(pk, axis=-1)).flatten() * scale.flatten()
+        out[:, i] = data[:, i].copy() - low
+    return out.astype(data.dtype)
+
+
+def adaptivehfilt(data, travel_time_us, window_size):
+    """Vectorised restatement of adaptivehfilt (_RadarDataFiltering.py:19-90).
+
+    mean over the per-trace window via float64 prefix sums; ``filtfilt([.25]*4, 1, m)`` is the 7-tap
+    triangular kernel [1,2,3,4,3,2,1]/16 applied to the odd-extended mean trace (padlen 12 > 3 taps
+    of memory, so the lfilter_zi transients never reach the kept samples)."""
+    data = np.asarray(data)
+    S, T = data.shape
+    if S <= 12:
+        raise ValueError("The length of the input vector x must be greater than padlen, which is 12.")
+    d64 = data.astype(np.float64)
+    P = np.concatenate([np.zeros((S, 1)), np.cumsum(d64, axis=1)], axis=1)
+    lo = np.empty(T, dtype=np.int64)
+    hi = np.empty(T, dtype=np.int64)
+    for i in range(T):
+        lo[i], hi[i] = adaptive_window(i, T, window_size)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        m = (P[:, hi] - P[:, lo]) / (hi - lo)[None, :]
+    ext = np.concatenate([2 * m[0:1] - m[3:0:-1], m, 2 * m[-1:] - m[-2:-5:-1]], axis=0)
+    c = np.array([1, 2, 3, 4, 3, 2, 1]) / 16.
+    low = sum(c[j] * ext[j:j + S] for j in range(7))
+    out = d64 - low * exp_taper(travel_time_us)[:, None]
+    return out.astype(data.dtype)
+
+
+def bandpass_coefficients(low_mhz, high_mhz, dt, order=5, filttype='butter', cheb_rp=5):
+    """Corner frequencies and (b, a) of vertical_band_pass, _RadarDataFiltering.py:510-535."""
+    from scipy.signal import butter, cheby1, bessel
+    nyq = 0.5 * (1.0 / dt)
+    corner = np.zeros((2,))
+    corner[0] = low_mhz * 1.0e6 / nyq
+    corner[1] = high_mhz * 1.0e6 / nyq
+    ft = filttype.lower()
+    if ft in ['butter', 'butterworth']:
+        return butter(order, corner, 'bandpass')
+    if ft in ['cheb', 'chebyshev']:
+        return cheby1(order, cheb_rp, corner, 'bandpass')
+    if ft == 'bessel':
+        return bessel(order, corner, 'bandpass')
+    raise ValueError('Filter type {:s} is not recognized'.format(filttype))
+
+
+def vertical_band_pass(data, dt, low_mhz, high_mhz, order=5, filttype='butter', cheb_rp=5,
+                       fir_window='hamming'):
+    """_RadarDataFiltering.py:469-549 (data part; flags are host bookkeeping)."""
+    from scipy.signal import filtfilt, firwin, lfilter
+    data = np.asarray(data)
+    if filttype.lower() == 'fir':
+        nyq = 0.5 * (1.0 / dt)
+        corner = np.array([low_mhz * 1.0e6 / nyq, high_mhz * 1.0e6 / nyq])
+        taps = firwin(order + 1, corner, pass_zero=False)
+        out = np.array(data, copy=True)
+        out[:-order, :] = lfilter(taps, 1.0, data, axis=0).astype(data.dtype)[order:, :]
+        return out
+    b, a = bandpass_coefficients(low_mhz, high_mhz, dt, order, filttype, cheb_rp)
+    return filtfilt(b, a, data, axis=0).astype(data.dtype)
+
+
+def filtfilt_explicit(b, a, x, padlen=None):
+    """scipy.signal.filtfilt(b, a, x, axis=0) (padtype='odd', method='pad') written out as the plain
+    transposed direct-form-II recurrence the CUDA kernel implements; used to pin the recurrence
+    itself (state layout, zi scaling, odd extension) against scipy."""
+    from scipy.signal import lfilter_zi
+    b = np.atleast_1d(np.asarray(b, dtype=np.float64))
+    a = np.atleast_1d(np.asarray(a, dtype=np.float64))
+    n = max(len(a), len(b))
+    if padlen is None:
+        padlen = 3 * n
+    bb = np.zeros(n)
+    aa = np.zeros(n)
+    bb[:len(b)] = b / a[0]
+    aa[:len(a)] = a / a[0]
+    zi = lfilter_zi(bb, aa) if n > 1 else np.zeros(0)
+    x = np.asarray(x, dtype=np.float64)
+    S = x.shape[0]
+    if S <= padlen:
+        raise ValueError("The length of the input vector x must be greater than padlen, which is %d." % padlen)
+    ext = np.concatenate([2 * x[0:1] - x[padlen:0:-1], x, 2 * x[-1:] - x[-2:-padlen - 2:-1]], axis=0)
+
+    def run(sig):
+        z = zi[:, None] * sig[0][None, :] if sig.ndim == 2 else zi * sig[0]
+        y = np.empty_like(sig)
+        for k in range(sig.shape[0]):
+            xk = sig[k]
+            yk = bb[0] * xk + (z[0] if n > 1 else 0.0)
+            for i in range(n - 2):
+                z[i] = bb[i + 1] * xk - aa[i + 1] * yk + z[i + 1]
+            if n > 1:
+                z[n - 2] = bb[n - 1] * xk - aa[n - 1] * yk
+            y[k] = yk
+        return y
+
+    y = run(ext)
+    y = run(y[::-1])[::-1]
+    return y[padlen:padlen + S]

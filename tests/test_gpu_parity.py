@@ -1,0 +1,136 @@
+"""Parity of the CUDA path (through the host mirrors -> C ABI) against the golden vectors produced by the
+unmodified reference and against the oracle.  Tolerance (BASELINE.json north_star): relative L2 <= 1e-5 for
+the fp32 device path against the reference's float64 output, max-abs reported; shapes, dtypes-on-return
+and flags exact."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, max_abs, rel_l2
+from util import dat_from_golden, synthetic_dat
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _report(name, got, want):
+    r, m = rel_l2(got, want), max_abs(got, want)
+    print("%-28s rel-L2 %.3e  max-abs %.3e" % (name, r, m))
+    return r
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_kirch_"))
+def test_kirchhoff_golden(name):
+    g = load_golden(name)
+    d = dat_from_golden(g)
+    d.migrate(mtype='kirch', vel=float(g["vel"]), nearfield=bool(g["nearfield"]))
+    assert d.data.dtype == np.float64 and d.data.shape == g["out"].shape
+    assert d.flags.mig == 'kirch'
+    assert _report(name, d.data, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_stolt"))
+def test_stolt_golden(name):
+    g = load_golden(name)
+    d = dat_from_golden(g)
+    d.migrate(mtype='stolt', vel=float(g["vel"]), htaper=float(g["htaper"]), vtaper=float(g["vtaper"]))
+    assert d.data.shape == g["out"].shape
+    assert d.data.dtype == (np.float32 if g["data"].dtype == np.float32 else np.float64)
+    assert _report(name, d.data, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_phsh_"))
+def test_phase_shift_golden(name):
+    g = load_golden(name)
+    d = dat_from_golden(g, dtype=np.float64)
+    vel = g["vel"] if g["vel"].ndim else float(g["vel"])
+    from impdar_b200 import migrationlib
+    migrationlib.migrationPhaseShift(d, vel=vel, htaper=float(g["htaper"]), vtaper=float(g["vtaper"]))
+    assert d.data.dtype == np.float64 and d.data.shape == g["out"].shape
+    assert _report(name, d.data, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_tk"))
+def test_tk_golden(name):
+    g = load_golden(name)
+    d = dat_from_golden(g)
+    d.migrate(mtype='tk', htaper=float(g["htaper"]), vtaper=float(g["vtaper"]))
+    assert d.flags.mig == 'tk'
+    assert _report(name, d.data, g["out"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_hfilt"))
+def test_hfilt_golden(name):
+    g = load_golden(name)
+    d = dat_from_golden(g)
+    d.hfilt(ftype='hfilt', bounds=(int(g["ntr1"]), int(g["ntr2"])))
+    assert d.data.dtype == g["out"].dtype
+    assert np.all(d.flags.hfilt == 1)
+    assert _report(name, d.data, g["out"]) < 1e-14
+    if "target" in g:  # the reference's exact known-answer test, test_RadarDataFiltering.py:53-57
+        assert np.all(d.data == g["target"])
+    d32 = dat_from_golden(g, dtype=np.float32)
+    d32.horizontalfilt(int(g["ntr1"]), int(g["ntr2"]))
+    assert d32.data.dtype == np.float32
+    assert rel_l2(d32.data, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_ahfilt_"))
+def test_ahfilt_golden(name):
+    g = load_golden(name)
+    d = dat_from_golden(g)
+    d.hfilt(ftype='adaptive', window_size=int(g["window_size"]))
+    assert d.flags.hfilt[0] == 1 and d.flags.hfilt[1] == 4
+    assert _report(name, d.data, g["out"]) < 1e-13
+    d32 = dat_from_golden(g, dtype=np.float32)
+    d32.adaptivehfilt(int(g["window_size"]))
+    assert d32.data.dtype == np.float32
+    assert rel_l2(d32.data, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_vbp_"))
+def test_vbp_golden(name):
+    g = load_golden(name)
+    d = dat_from_golden(g)
+    d.vertical_band_pass(float(g["low"]), float(g["high"]), order=int(g["order"]), filttype=str(g["filttype"]))
+    assert d.flags.bpass[0] == 1 and d.flags.bpass[1] == float(g["low"]) and d.flags.bpass[2] == float(g["high"])
+    assert _report(name, d.data, g["out"]) < 1e-6   # the recurrence itself differs ~1e-9 between fp64 orderings
+    d32 = dat_from_golden(g, dtype=np.float32)
+    d32.vertical_band_pass(float(g["low"]), float(g["high"]), order=int(g["order"]), filttype=str(g["filttype"]))
+    assert d32.data.dtype == np.float32
+    assert _report(name + "[f32]", d32.data, g["out"]) < TOL
+
+
+def test_noinit_fixtures():
+    """The reference's own fixtures: zeros(10, 20) through every migration (test_migrationlib.py:103-135)."""
+    import impdar_b200
+    from impdar_b200 import migrationlib
+
+    def big():
+        d = impdar_b200.RadarData(np.zeros((10, 20)), dt=1, travel_time=np.arange(10), dist=np.arange(20),
+                                  trace_int=1)
+        return d
+    for fn in (migrationlib.migrationStolt, migrationlib.migrationKirchhoff,
+               migrationlib.migrationTimeWavenumber, migrationlib.migrationPhaseShift):
+        d = fn(big())
+        assert np.all(d.data == 0)
+    d = big()
+    d.data = d.data.astype(int)
+    d = migrationlib.migrationStolt(d)
+    assert np.all(d.data == 0) and d.data.dtype == np.float64
+    d = big()
+    d.data = np.ones((1, 1))
+    with pytest.raises(ValueError):
+        migrationlib.migrationStolt(d)
+    with pytest.raises(TypeError):
+        migrationlib.migrationPhaseShift(big(), vel_fn='notafile.txt')
+
+
+def test_bad_mtype_and_ftype():
+    d = synthetic_dat(32, 16)
+    with pytest.raises(ValueError):
+        d.migrate(mtype='dummy')
+    with pytest.raises(ValueError):
+        d.hfilt(ftype='dummy')
+    with pytest.raises(ValueError):
+        d.vertical_band_pass(0.1, 100., filttype='dummy')

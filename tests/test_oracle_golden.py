@@ -1,0 +1,91 @@
+"""The oracle (oracle/*.py) must reproduce the golden vectors, which are outputs of the unmodified
+reference (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, rel_l2
+from oracle import filtering as of
+from oracle import migration as om
+
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_kirch_"))
+def test_kirchhoff(name):
+    g = load_golden(name)
+    if g["data"].size > 40000:
+        pytest.skip("oracle Kirchhoff on the tutorial radargram is covered by the gpu suite's golden check")
+    out = om.kirchhoff(g["data"], g["travel_time"], g["dist"], float(g["vel"]), bool(g["nearfield"]))
+    assert rel_l2(out, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_stolt"))
+def test_stolt(name):
+    g = load_golden(name)
+    _, out = om.stolt(g["data"].astype(np.float64), float(g["dt"]), g["trace_int"], g["dist"], float(g["vel"]),
+                      float(g["htaper"]), float(g["vtaper"]))
+    tol = 2e-6 if g["out"].dtype == np.float32 else TOL   # tutorial fixture: float32 in the reference itself
+    assert out.shape == g["out"].shape
+    assert rel_l2(out, g["out"]) < tol
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_phsh_"))
+def test_phase_shift(name):
+    g = load_golden(name)
+    if g["data"].size > 40000:
+        pytest.skip("too slow for the CPU suite")
+    _, out = om.phase_shift(g["data"].astype(np.float64), float(g["dt"]), g["travel_time"], g["trace_int"],
+                            g["dist"], g["vel"] if g["vel"].ndim else float(g["vel"]),
+                            float(g["htaper"]), float(g["vtaper"]))
+    assert rel_l2(out, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_tk"))
+def test_time_wavenumber(name):
+    g = load_golden(name)
+    out = om.time_wavenumber(g["data"], float(g["htaper"]), float(g["vtaper"]))
+    assert np.array_equal(out, g["out"])
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_hfilt"))
+def test_hfilt(name):
+    g = load_golden(name)
+    out = of.horizontalfilt(g["data"], g["travel_time"], int(g["ntr1"]), int(g["ntr2"]))
+    assert np.array_equal(out, g["out"])
+    if "target" in g:   # the reference's exact known-answer fixture (test_RadarDataFiltering.py:53-57)
+        assert np.all(out == g["target"])
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_ahfilt_"))
+def test_ahfilt(name):
+    g = load_golden(name)
+    out = of.adaptivehfilt(g["data"], g["travel_time"], int(g["window_size"]))
+    assert rel_l2(out, g["out"]) < TOL
+    out2 = of.adaptivehfilt_loops(g["data"], g["travel_time"], int(g["window_size"]))
+    assert np.array_equal(out2, g["out"])
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_vbp_"))
+def test_vbp(name):
+    g = load_golden(name)
+    out = of.vertical_band_pass(g["data"], float(g["dt"]), float(g["low"]), float(g["high"]),
+                                order=int(g["order"]), filttype=str(g["filttype"]))
+    assert np.array_equal(out, g["out"])
+    if str(g["filttype"]) != "fir":
+        b, a = of.bandpass_coefficients(float(g["low"]), float(g["high"]), float(g["dt"]),
+                                        order=int(g["order"]), filttype=str(g["filttype"]))
+        assert rel_l2(of.filtfilt_explicit(b, a, g["data"]), g["out"]) < 1e-6
+
+
+def test_loop_flavours_match():
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((24, 20))
+    tt = np.arange(24) * 0.01
+    dist = np.arange(20) * 0.005
+    a = om.kirchhoff(x, tt, dist, 1.69e8, True)
+    b = om.kirchhoff_loops(x, tt, dist, 1.69e8, True)
+    assert rel_l2(a, b) < 1e-14
+    _, s1 = om.stolt(x, 1e-8, np.ones(20) * 5., dist, 1.68e8, 3, 4)
+    _, s2 = om.stolt_loops(x, 1e-8, np.ones(20) * 5., dist, 1.68e8, 3, 4)
+    assert rel_l2(s1, s2) < 1e-12
+    assert om.kirchhoff_pair_count(tt, dist, 1.69e8) > 0
