@@ -9,7 +9,9 @@
 //   out = ifft_k(TK).real                                                                   (:282)
 //
 // Data are real, so FK(-w,-k) = conj FK(w,k) and TK(tau,-k) = conj TK(tau,k): only k = 0..tnum/2 is
-// computed (R2C along traces, C2C along time, C2R back), halving the work.
+// computed (R2C along traces, C2C along time, C2R back), halving the work.  One bin breaks the symmetry:
+// the Nyquist frequency (fftfreq's -nt/2) has no +nt/2 partner, so TK is not exactly Hermitian and the
+// reference's ``.real`` symmetrises it; for that bin this means FK * Re(cp^(tau+1)), i.e. the cosine only.
 //
 // The contraction over w is a per-kx non-uniform DFT (the "matrix" depends on kx), i.e. there is no
 // operand shared between columns, so it is kept as complex FMA on the SIMT pipes:
@@ -81,9 +83,10 @@ __device__ __forceinline__ void ps_park(float2 part, float2 (*buf)[PS_THREADS / 
 }
 
 // Sum the warps' parked partials of one tau block and store (or accumulate) TK.
+// `nyq_const` adds the constant-velocity Nyquist-frequency term FK[nt/2,k] * cos((tau+1) phi) (see header).
 template <int COLS>
 __device__ __forceinline__ void ps_commit(const PhshParams &p, float2 (*buf)[PS_THREADS / 32][COLS], int tb0,
-                                          bool accumulate) {
+                                          bool accumulate, bool nyq_const = false) {
     __syncthreads();
     for (int i = threadIdx.x; i < PS_TB * COLS; i += PS_THREADS) {
         const int b = i / COLS, c = i % COLS;
@@ -94,6 +97,17 @@ __device__ __forceinline__ void ps_commit(const PhshParams &p, float2 (*buf)[PS_
             for (int w = 0; w < PS_THREADS / 32; ++w) {
                 s.x += buf[b][w][c].x;
                 s.y += buf[b][w][c].y;
+            }
+            if (nyq_const && p.nt >= 2) {
+                const double w = ps_omega(p.nt / 2, p.nt, p.dt);
+                const double vk = p.vel * ps_kx(kk, p.T, p.dx) / 2.0;
+                if (vk * vk < w * w) {
+                    const double phi = w * p.dt * sqrt(1.0 - vk * vk / (w * w));
+                    const float cn = (float)cos((double)(tau + 1) * phi);
+                    const float2 f = p.FK[(size_t)(p.nt / 2) * p.K + kk];
+                    s.x = fmaf(f.x, cn, s.x);
+                    s.y = fmaf(f.y, cn, s.y);
+                }
             }
             s.x *= p.inv_s;
             s.y *= p.inv_s;
@@ -132,7 +146,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) phsh_const_kernel(const __grid_
         for (int i = 0; i < PSC_PER; ++i) {
             const int iw = ch * PSC_WCHUNK + (tid / PSC_COLS) + i * (PS_THREADS / PSC_COLS);
             float2 g = make_float2(0.f, 0.f), zz = make_float2(1.f, 0.f), z64 = zz;
-            if (kvalid && iw < p.nt) {
+            if (kvalid && iw < p.nt && !(p.nt >= 2 && iw == p.nt / 2)) {  // the Nyquist bin is added at commit
                 const double w = ps_omega(iw, p.nt, p.dt);
                 if (vkx2 < w * w) {  // propagating (:412)
                     const double phi = w * p.dt * sqrt(1.0 - vkx2 / (w * w));  // = -phase (:415); cp = e^{+i phi}
@@ -166,7 +180,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) phsh_const_kernel(const __grid_
 #pragma unroll
             for (int i = 0; i < PSC_PER; ++i)
                 G[i * PS_THREADS + tid] = cmulf(G[i * PS_THREADS + tid], Z64[i * PS_THREADS + tid]);
-            ps_commit<PSC_COLS>(p, buf, tb0, ch > 0);
+            ps_commit<PSC_COLS>(p, buf, tb0, ch > 0, ch == 0);
         }
     }
 }
@@ -184,6 +198,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) phsh_layered_kernel(const __gri
     for (int ch = 0; ch * PSL_WCHUNK < p.nt; ++ch) {
         float2 fk0[PSL_PER];
         double c[PSL_PER], wturn[PSL_PER], phase[PSL_PER];
+        unsigned nyq_slot = 0;  // bit i set: state i is the Nyquist bin, which contributes FK * cos(phase) only
 #pragma unroll
         for (int i = 0; i < PSL_PER; ++i) {
             const int iw = ch * PSL_WCHUNK + tid + i * PS_THREADS;
@@ -197,6 +212,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) phsh_layered_kernel(const __gri
                 c[i] = h * h;                                        // coss = 1 - c * v^2   (:460)
                 wturn[i] = w * p.dt * 0.15915494309189535;           // phase advance in turns per unit sqrt(coss)
                 fk0[i] = p.FK[(size_t)iw * p.K + k];
+                if (p.nt >= 2 && iw == p.nt / 2) nyq_slot |= 1u << i;
             }
         }
         for (int tb0 = 0; tb0 < p.S; tb0 += PS_TB) {
@@ -222,6 +238,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) phsh_layered_kernel(const __gri
                         const double fr = phase[i] - rint(phase[i]);
                         float sn, cs;
                         __sincosf((float)fr * 6.283185307179586f, &sn, &cs);
+                        if ((nyq_slot >> i) & 1u) sn = 0.f;
                         part.x += fmaf(fk0[i].x, cs, -fk0[i].y * sn);
                         part.y += fmaf(fk0[i].x, sn, fk0[i].y * cs);
                     }

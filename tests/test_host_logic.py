@@ -1,0 +1,162 @@
+"""Host-side logic of the product (no GPU): argument preparation, dispatch, error behaviour, the seam."""
+import sys
+from unittest.mock import MagicMock, patch
+
+import numpy as np
+import pytest
+
+import impdar_b200
+from impdar_b200 import filtering, migrationlib, parallel
+from oracle import filtering as of
+from oracle import migration as om
+
+
+def test_gradient_coefficients_match_numpy():
+    rng = np.random.default_rng(0)
+    f = rng.standard_normal((17, 5))
+    for x in (np.arange(17) * 0.01 / 1e6,                    # arange*dt: numpy's non-uniform branch
+              np.arange(17) * 0.5,                           # exactly uniform branch
+              np.cumsum(0.5 + rng.random(17)),               # irregular
+              np.array([0.0, 1.0])):                         # two samples
+        ff = f[:len(x)]
+        c = migrationlib.gradient_coefficients(x)
+        g = np.zeros_like(ff)
+        for s in range(len(x)):
+            if s > 0:
+                g[s] += c[0, s] * ff[s - 1]
+            g[s] += c[1, s] * ff[s]
+            if s < len(x) - 1:
+                g[s] += c[2, s] * ff[s + 1]
+        assert np.allclose(g, np.gradient(ff, x, axis=0), rtol=1e-13, atol=0)
+    c = migrationlib.gradient_coefficients(np.arange(9) * 0.5)
+    assert np.all(c[1, 1:-1] == 0)                           # uniform branch never reads f[s]
+    with pytest.raises(ValueError):
+        migrationlib.gradient_coefficients(np.array([1.0]))
+
+
+def test_iir_prepare_matches_scipy_filtfilt():
+    from scipy.signal import butter, filtfilt
+    b, a = butter(5, [0.04, 0.2], 'bandpass')
+    bb, aa, zi, padlen = filtering.iir_prepare(b, a)
+    assert padlen == 33 and len(bb) == 11 and aa[0] == 1.0 and len(zi) == 10
+    x = np.random.default_rng(1).standard_normal((120, 3))
+    assert np.allclose(of.filtfilt_explicit(bb, aa, x, padlen), filtfilt(b, a, x, axis=0), rtol=0, atol=1e-6)
+    bb, aa, zi, padlen = filtering.iir_prepare([.25, .25, .25, .25], 1)
+    assert padlen == 12 and np.allclose(aa, [1, 0, 0, 0])
+
+
+def test_hfilt_bounds_like_reference():
+    for n1, n2, T in [(0, 100, 400), (-5, 10, 50), (60, 10, 50), (3, 1000, 50), (49, 49, 50)]:
+        assert of.hfilt_bounds(n1, n2, T) == (int(max(0, min(n1, T - 1))), int(max(int(max(0, min(n1, T - 1))) + 1, min(n2, T))))
+
+
+def test_velocity_profile_matches_oracle_and_errors():
+    d = impdar_b200.RadarData(np.zeros((10, 20)), dt=1, travel_time=np.arange(10) / 10., dist=np.arange(20), trace_int=1)
+    assert migrationlib.getVelocityProfile(d, 1.68e8) == 1.68e8
+    layers = np.array([[1.677e8, 0], [1.677e8, 50], [1.2e8, 51], [2.2e8, 100]])
+    v = migrationlib.getVelocityProfile(d, layers)
+    assert np.allclose(v, om.get_velocity_profile_layered(d.travel_time, layers), rtol=1e-14)
+    twod = 1.68e8 * np.ones((10, 2)); twod[:, 1] = 0.
+    for bad in (twod, 1.68e8 * np.ones((8,)), 1.68e8 * np.ones((8, 1)), 1.68e8 * np.ones((1, 2)), 1.68e8 * np.ones((8, 4))):
+        with pytest.raises(ValueError):
+            migrationlib.getVelocityProfile(d, bad)
+    d.dist = None
+    with pytest.raises(ValueError):
+        migrationlib.getVelocityProfile(d, np.ones((5, 3)))
+
+
+def test_check_data_shape():
+    d = impdar_b200.RadarData(np.zeros((10, 20)), dt=1, travel_time=np.arange(10), dist=np.arange(20), trace_int=1)
+    migrationlib._check_data_shape(d)
+    d.data = np.ones((1, 1))
+    with pytest.raises(ValueError):
+        migrationlib._check_data_shape(d)
+
+
+def _dat():
+    return impdar_b200.RadarData(np.ones((50, 40)), dt=1e-9, travel_time=0.001 * np.arange(50) + 0.001,
+                                 dist=np.arange(40) * 1e-3, trace_int=np.ones(40))
+
+
+def test_migrate_forwards_exact_kwargs():
+    """Mirror of the reference's seam contract, test_RadarDataFiltering.py:291-331."""
+    with patch('impdar_b200.migrationlib.migrationKirchhoff') as m:
+        d = _dat(); d.migrate(mtype='kirch', vel=10., nearfield=False)
+        m.assert_called_with(d, vel=10., nearfield=False)
+        assert d.flags.mig == 'kirch'
+    with patch('impdar_b200.migrationlib.migrationStolt') as m:
+        d = _dat(); d.migrate(mtype='stolt', htaper=1, vtaper=2, vel=999.)
+        m.assert_called_with(d, htaper=1, vtaper=2, vel=999.)
+    with patch('impdar_b200.migrationlib.migrationPhaseShift') as m:
+        d = _dat(); d.migrate(mtype='phsh', vel=1., vel_fn='dummy', htaper=1, vtaper=2)
+        m.assert_called_with(d, vel=1., vel_fn='dummy', htaper=1, vtaper=2)
+    with patch('impdar_b200.migrationlib.migrationTimeWavenumber') as m:
+        d = _dat(); d.migrate(mtype='tk', vel=1., vel_fn='dummy', htaper=1, vtaper=2)
+        m.assert_called_with(d, vel=1., vel_fn='dummy', htaper=1, vtaper=2)
+    with pytest.raises(ValueError):
+        _dat().migrate(mtype='dummy')
+    with pytest.raises(Exception):
+        _dat().migrate(mtype='su_dummy')
+
+
+def test_hfilt_wrapper_dispatch():
+    """test_RadarDataFiltering.py:249-266."""
+    d = _dat(); d.adaptivehfilt = MagicMock()
+    d.hfilt(ftype='adaptive', window_size=1000)
+    d.adaptivehfilt.assert_called_with(window_size=1000)
+    d = _dat(); d.horizontalfilt = MagicMock()
+    d.hfilt(ftype='hfilt', bounds=(0, 100))
+    d.horizontalfilt.assert_called_with(0, 100)
+    with pytest.raises(ValueError):
+        _dat().hfilt(ftype='dummy')
+    with pytest.raises(ValueError):
+        _dat().vertical_band_pass(0.1, 100., filttype='dummy')
+
+
+def test_no_gpu_means_error_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _dat().migrate(mtype='stolt')
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _dat().horizontalfilt(0, 10)
+
+
+def test_kirchhoff_ranges_cover_and_balance():
+    tt = np.arange(512) * 0.01
+    dist = np.arange(4096) * 0.005
+    for world in (1, 2, 3, 4, 8):
+        r = parallel.kirchhoff_output_ranges(4096, world, tt, dist, 1.69e8)
+        assert r[0][0] == 0 and r[-1][1] == 4096
+        assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+        assert all(b % 8 == 0 for b, _ in r)
+        cost = parallel.kirchhoff_trace_cost(tt, dist, 1.69e8)
+        shares = [cost[b:e].sum() for b, e in r]
+        assert max(shares) / (sum(shares) / world) < 1.1
+    assert parallel.profiles_for_rank(10, 1, 4) == [1, 5, 9]
+
+
+@pytest.mark.reference
+def test_install_rebinds_reference_seam():
+    from oracle._refimport import import_reference
+    mig_python, RefRadarData, NoInit = import_reference()
+    import impdar.lib.migrationlib as ref_mig
+    orig = ref_mig.migrationStolt
+    impdar_b200.install()
+    try:
+        assert ref_mig.migrationStolt is migrationlib.migrationStolt
+        assert ref_mig.migrationKirchhoff is migrationlib.migrationKirchhoff
+        assert RefRadarData.vertical_band_pass is filtering.vertical_band_pass
+        # the reference's own wrapper tests still hold with the backend installed
+        with patch('impdar.lib.migrationlib.migrationKirchhoff') as m:
+            rd = NoInit.NoInitRadarDataFiltering()
+            rd.migrate(mtype='kirch', vel=10., nearfield=False)
+            assert m.call_args.kwargs == dict(vel=10., nearfield=False)
+        rd = NoInit.NoInitRadarDataFiltering()
+        rd.horizontalfilt = MagicMock()
+        rd.hfilt(ftype='hfilt', bounds=(0, 100))
+        rd.horizontalfilt.assert_called_with(0, 100)
+    finally:
+        impdar_b200.uninstall()
+    assert ref_mig.migrationStolt is orig
