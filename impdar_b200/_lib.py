@@ -35,6 +35,8 @@ PROTOTYPES = {
                                       _vp, _c_sz, _vp]),
     "impdar_kirchhoff_enable_stats": (_c_int, [_c_int]),
     "impdar_kirchhoff_last_stats": (_c_int, [_vp, _vp]),
+    "impdar_kirchhoff_set_mode": (_c_int, [_c_int]),
+    "impdar_kirchhoff_last_path": (_c_int, []),
     "mig_kirch_loop": (None, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _vp, _c_dbl, _c_int]),
     "impdar_kirchhoff_host_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp, _c_dbl, _c_int]),
     "impdar_stolt_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int]),

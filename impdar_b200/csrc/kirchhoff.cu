@@ -36,6 +36,7 @@ struct KirchParams {
     double vel, tmax, tt0, inv_dt, cs;  // cs = 2/(vel*dt_eff)
     float neg_u0, thr, wfar, wnear;     // thr = 0.5 - delta ; wfar = 1/(2 pi vel) ; wnear = 4/(vel dt)^2/(2 pi)
     int monotone;                       // dist ascending -> per-sample aperture by binary search
+    int rowmajor, Tp, Apad;             // table path: gradT/dataT are (S, Tp) row-major, trace x at column Apad + x
 };
 
 #define KIRCH_MAGIC 12582912.0f  // 1.5 * 2^23
@@ -78,11 +79,12 @@ __device__ __forceinline__ float exact_term(const KirchParams &p, int ti, int x,
     if (t > p.tmax) return 0.f;
     const int k = exact_pick(p.tt, p.S, t, p.tt0, p.inv_dt);
     const double costheta = p.zs[ti] / rs;
-    const double g = (double)p.gradT[(size_t)x * p.SP + k];
+    const size_t gi = p.rowmajor ? (size_t)k * p.Tp + p.Apad + x : (size_t)x * p.SP + k;
+    const double g = (double)p.gradT[gi];
     double term = g * costheta / p.vel;
     if (term != term) term = 0.0;
     if (NEAR) {
-        const double dv = (double)p.dataT[(size_t)x * p.SP + k];
+        const double dv = (double)p.dataT[gi];
         double tn = dv * costheta / (rs * rs);
         if (tn == tn) term += tn;
     }
@@ -91,9 +93,77 @@ __device__ __forceinline__ float exact_term(const KirchParams &p, int ti, int x,
 
 #define KQ_CAP 192
 
+// Fast path over one staged chunk of <= 32 input traces (4 per iteration, straight-line, predicated).
+template <bool NEAR, bool STATS, bool HASNAN, typename Flush>
+__device__ __forceinline__ void kirch_chunk(Flush &flush, const float *__restrict__ gT, const float *__restrict__ dT,
+                                            const float *__restrict__ sCw, int *__restrict__ sQw, int jend,
+                                            unsigned rowoff, unsigned SP, unsigned kmax, int rel, unsigned span,
+                                            int xb, int lane, float u2, float Uw, float Un, float neg_u0, float thr,
+                                            float &acc0, float &acc1, int &qn, unsigned &npairs, unsigned &nexact) {
+#pragma unroll 1
+    for (int j0 = 0; j0 < jend; j0 += 4) {
+        const float4 c4 = *reinterpret_cast<const float4 *>(sCw + j0);
+        const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+        unsigned amb4 = 0;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const float q = u2 + c[jj];
+            const float s = rsqrt_approx(q);
+            const float f = fmaf(q, s, neg_u0);
+            const float r = f + KIRCH_MAGIC;
+            const unsigned k = min((unsigned)(__float_as_int(r) - KIRCH_MAGIC_I), kmax);
+            const float e = f - (r - KIRCH_MAGIC);
+            const bool inr = (unsigned)(rel + j0 + jj) <= span;
+            const bool amb = fabsf(e) > thr;
+            const unsigned idx = rowoff + (unsigned)jj * SP + k;
+            const float g = __ldg(gT + idx);
+            const bool ok = inr && !amb;
+            if (!HASNAN) {
+                // select on the weight so the accumulate is a single FFMA
+                const float w = ok ? Uw * s : 0.f;
+                if (jj & 1) acc1 = fmaf(g, w, acc1); else acc0 = fmaf(g, w, acc0);
+                if (NEAR) {
+                    const float dv = __ldg(dT + idx);
+                    const float wn = ok ? (Un * s) * (s * s) : 0.f;
+                    if (jj & 1) acc1 = fmaf(dv, wn, acc1); else acc0 = fmaf(dv, wn, acc0);
+                }
+            } else {
+                float term = g * (Uw * s);
+                if (term != term) term = 0.f;   // nansum skips NaN terms (mig_python.py:53)
+                if (NEAR) {
+                    const float dv = __ldg(dT + idx);
+                    const float tn = dv * ((Un * s) * (s * s));
+                    if (tn == tn) term += tn;
+                }
+                if (jj & 1) acc1 += ok ? term : 0.f; else acc0 += ok ? term : 0.f;
+            }
+            if (STATS && inr) ++npairs;
+            amb4 |= (inr && amb) ? (1u << jj) : 0u;
+        }
+        rowoff += 4u * SP;
+        if (__any_sync(0xffffffffu, amb4 != 0)) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const bool a = (amb4 >> jj) & 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, a);
+                if (a) {
+                    sQw[qn + __popc(m & ((1u << lane) - 1u))] = ((xb + j0 + jj) << 5) | lane;
+                    ++nexact;
+                }
+                qn += __popc(m);
+            }
+            if (qn > 32) {  // keep the queue below KQ_CAP: at most 128 entries are added per group of 4
+                __syncwarp();
+                flush(qn);
+                qn = 0;
+            }
+        }
+    }
+}
+
 template <bool NEAR, bool STATS>
 __global__ void __launch_bounds__(256) kirch_general_kernel(const __grid_constant__ KirchParams p) {
-    __shared__ float sC[8][32];
+    __shared__ __align__(16) float sC[8][32];
     __shared__ int sQ[8][KQ_CAP];
     __shared__ float sT[8][32];
     __shared__ int sO[8][32];
@@ -114,9 +184,9 @@ __global__ void __launch_bounds__(256) kirch_general_kernel(const __grid_constan
         const double dxi = p.dist[xi];
         const int tic = active ? ti : p.S - 1;
         const double zs2i = p.zs2[tic];
-        const float U = (float)(p.tt[tic] * p.inv_dt);
-        float u2 = (float)((p.tt[tic] * p.inv_dt) * (p.tt[tic] * p.inv_dt));
-        u2 = fmaxf(u2, 1e-30f);  // q == 0 only at the apex of a zero-depth sample: weight is 0 there
+        const double Ud = p.tt[tic] * p.inv_dt;
+        const float U = (float)Ud;
+        const float u2 = fmaxf((float)(Ud * Ud), 1e-30f);  // q == 0 only at the apex of a zero-depth sample (weight 0)
 
         // exact per-sample aperture [xlo, xhi]: pairs with 2r/v > max(tt) contribute exactly 0
         int xlo = xi + 1, xhi = xi;
@@ -148,9 +218,14 @@ __global__ void __launch_bounds__(256) kirch_general_kernel(const __grid_constan
             xlo_w = min(xlo_w, __shfl_xor_sync(0xffffffffu, xlo_w, o));
             xhi_w = max(xhi_w, __shfl_xor_sync(0xffffffffu, xhi_w, o));
         }
-        const unsigned span = (unsigned)(xhi - xlo);  // xhi < xlo -> huge unsigned? no: xlo = xi+1, xhi = xi -> 0xffffffff
-        const bool lane_empty = xhi < xlo;
+        unsigned span = (unsigned)(xhi - xlo);
+        if (xhi < xlo) {  // empty aperture: make the range test fail for every x
+            span = 0;
+            xlo = 0x40000000;
+        }
         const float thr = p.monotone ? p.thr : -1.f;  // non-monotone positions: every pair takes the exact path
+        const float Uw = U * p.wfar, Un = U * p.wnear;
+        const unsigned SP = (unsigned)p.SP, kmax = SP - 1u;
         int qn = 0;
 
         auto flush = [&](int count) {
@@ -184,61 +259,15 @@ __global__ void __launch_bounds__(256) kirch_general_kernel(const __grid_constan
                 sC[warp][lane] = c2v;
                 __syncwarp();
             }
-            const int n = min(32, xhi_w - xb + 1);
-            const float *gp = p.gradT + (size_t)xb * p.SP;
-            const float *dp = NEAR ? p.dataT + (size_t)xb * p.SP : nullptr;
-            for (int j0 = 0; j0 < n; j0 += 4) {
-                unsigned ambmask = 0;
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int j = j0 + jj;
-                    if (j < n) {
-                        const float c2 = sC[warp][j];
-                        const float q = u2 + c2;
-                        const float s = rsqrt_approx(q);
-                        const float f = fmaf(q, s, p.neg_u0);
-                        const float r = f + KIRCH_MAGIC;
-                        const int k = (int)min((unsigned)(__float_as_int(r) - KIRCH_MAGIC_I), (unsigned)(p.SP - 1));
-                        const float e = f - (r - KIRCH_MAGIC);
-                        const bool inr = !lane_empty && ((unsigned)(xb + j - xlo) <= span);
-                        const bool amb = fabsf(e) > thr;
-                        const float g = __ldg(gp + (size_t)j * p.SP + k);
-                        const float w = U * s;
-                        if (inr && !amb) {
-                            float term = g * w * p.wfar;
-                            if (NEAR) {
-                                const float dv = __ldg(dp + (size_t)j * p.SP + k);
-                                float tn = dv * ((w * p.wnear) * (s * s));
-                                if (hasnan && tn != tn) tn = 0.f;
-                                if (hasnan && term != term) term = 0.f;
-                                term += tn;
-                            } else if (hasnan && term != term) {
-                                term = 0.f;
-                            }
-                            if (jj & 1) acc1 += term; else acc0 += term;
-                        }
-                        if (STATS && inr) ++npairs;
-                        if (inr && amb) ambmask |= 1u << jj;
-                    }
-                }
-                if (__any_sync(0xffffffffu, ambmask != 0)) {
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const bool a = (ambmask >> jj) & 1u;
-                        const unsigned m = __ballot_sync(0xffffffffu, a);
-                        if (a) {
-                            sQ[warp][qn + __popc(m & ((1u << lane) - 1u))] = ((xb + j0 + jj) << 5) | lane;
-                            ++nexact;
-                        }
-                        qn += __popc(m);
-                    }
-                    __syncwarp();
-                    if (qn > 32) {
-                        flush(qn);
-                        qn = 0;
-                    }
-                }
-            }
+            const int jend = (min(32, xhi_w - xb + 1) + 3) & ~3;   // padded entries fall outside every lane's range
+            const unsigned rowoff = (unsigned)xb * SP;
+            const int rel = xb - xlo;
+            if (hasnan)
+                kirch_chunk<NEAR, STATS, true>(flush, p.gradT, p.dataT, sC[warp], sQ[warp], jend, rowoff, SP, kmax, rel, span,
+                                               xb, lane, u2, Uw, Un, p.neg_u0, thr, acc0, acc1, qn, npairs, nexact);
+            else
+                kirch_chunk<NEAR, STATS, false>(flush, p.gradT, p.dataT, sC[warp], sQ[warp], jend, rowoff, SP, kmax, rel, span,
+                                                xb, lane, u2, Uw, Un, p.neg_u0, thr, acc0, acc1, qn, npairs, nexact);
         }
         __syncwarp();
         if (qn > 0) flush(qn);
@@ -315,11 +344,216 @@ __global__ void kirch_prep_vectors_kernel(const double *__restrict__ tt, double 
     }
 }
 
+// =====================================================================================================
+// Uniform-geometry path.  When traces are equally spaced (after ImpDAR's constant_space interpolation, or any
+// synthetic geometry) the travel time of a pair depends only on (output sample ti, trace offset m = |x - xi|),
+// so the nearest-sample pick k(ti, m) and the obliquity weight w(ti, m) are the same for every output trace.
+// They are tabulated once per call with the reference's float64 sequence (S x aperture entries), and the
+// migration becomes out[ti, xi] = sum_m w[ti,m] * (g[k[ti,m], xi-m] + g[k[ti,m], xi+m]): lanes run over
+// consecutive output traces, so every gather is a contiguous 128-byte row segment of the (zero-padded,
+// row-major) d/dt image and the inner loop is one load + half an FADD/FFMA per pair.
+// Table entries whose pick (or aperture cut) could change within the measured deviation of the real trace
+// positions from the uniform grid are flagged and re-evaluated per pair by the exact float64 path, so the
+// result is again the reference's pick for every pair.
+struct KirchTabParams {
+    const float *gP;    // (S, Tp): d/dt, trace x at column Apad + x, zero padded
+    const float *dP;    // (S, Tp): data (near field) or null
+    const int2 *tab;    // [S][A1]: {k or -1 (no contribution) or -2 (ambiguous), bits of the far weight}
+    const float *tabn;  // [S][A1]: near-field weight, or null
+    const int *nm;      // [S]: number of table entries to visit
+    float *out;
+    const int *flags;
+    unsigned long long *stats;
+    int S, T, Tp, Apad, A1, ldo, x_begin, x_end;
+};
+
+__global__ void __launch_bounds__(128) kirch_table_build_kernel(int2 *__restrict__ tab, float *__restrict__ tabn,
+                                                                int *__restrict__ nm, int S, int A1, double dxm,
+                                                                const double *__restrict__ zs,
+                                                                const double *__restrict__ zs2,
+                                                                const double *__restrict__ tt, double vel, double tmax,
+                                                                double tt0, double inv_dt, double eps_t) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ti = blockIdx.y;
+    if (m >= A1) return;
+    const double d = (double)m * dxm;
+    double rs;
+    const double t = exact_time(d, zs2[ti], vel, rs);
+    int k = -1;
+    float w = 0.f, wn = 0.f;
+    const bool in_lo = !((t - eps_t) > tmax), in_hi = !((t + eps_t) > tmax);
+    if (in_lo) {
+        if (!in_hi) {
+            k = -2;
+        } else {
+            const int k_lo = exact_pick(tt, S, t - eps_t, tt0, inv_dt);
+            const int k_hi = exact_pick(tt, S, t + eps_t, tt0, inv_dt);
+            k = (k_lo == k_hi) ? exact_pick(tt, S, t, tt0, inv_dt) : -2;
+        }
+        const double costheta = zs[ti] / rs;
+        const double wf = costheta / vel * 0.15915494309189535;
+        const double wq = costheta / (rs * rs) * 0.15915494309189535;
+        if (wf != wf) {
+            k = -1;  // 0/0 at the apex of a zero-depth sample: nansum drops the term (mig_python.py:53)
+        } else {
+            w = (float)wf;
+            wn = (float)wq;
+        }
+    }
+    tab[(size_t)ti * A1 + m] = make_int2(k, __float_as_int(w));
+    if (tabn) tabn[(size_t)ti * A1 + m] = wn;
+    if (k != -1) atomicMax(&nm[ti], m + 1);
+}
+
+// d/dt (np.gradient stencil) into the padded row-major layout; also the non-finite scan.
+__global__ void __launch_bounds__(256) grad_padded_kernel(const float *__restrict__ data, float *__restrict__ gP,
+                                                          float *__restrict__ dP, int S, int T, int Tp, int Apad,
+                                                          const double *__restrict__ coef, int *__restrict__ flags) {
+    const int s = blockIdx.y;
+    const double a = coef[s], b = coef[S + s], c = coef[2 * S + s];
+    bool bad = false;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < T; x += gridDim.x * blockDim.x) {
+        const float dv = data[(size_t)s * T + x];
+        double acc = 0.0;
+        if (s > 0 && a != 0.0) acc += a * (double)data[(size_t)(s - 1) * T + x];
+        if (b != 0.0) acc += b * (double)dv;
+        if (s < S - 1 && c != 0.0) acc += c * (double)data[(size_t)(s + 1) * T + x];
+        const float g = (float)acc;
+        if (!isfinite(g) || !isfinite(dv)) bad = true;
+        gP[(size_t)s * Tp + Apad + x] = g;
+        if (dP) dP[(size_t)s * Tp + Apad + x] = dv;
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, 1);
+}
+
+constexpr int KT_R = 4;  // output traces per thread (stride 32)
+
+template <bool NEAR, bool HASNAN, bool STATS, bool APEX>
+__device__ __forceinline__ void kirch_table_step(const KirchTabParams &p, const float *__restrict__ gbase,
+                                                 const float *__restrict__ dbase, int2 e, float wn, int m, int xbase,
+                                                 float (&acc)[KT_R], unsigned &npairs) {
+    const float w = __int_as_float(e.y);
+    const long long row = (long long)e.x * p.Tp;
+    const float *__restrict__ pl = gbase + (row - m);
+    const float *__restrict__ pr = gbase + (row + m);
+    const float *__restrict__ ql = NEAR ? dbase + (row - m) : nullptr;
+    const float *__restrict__ qr = NEAR ? dbase + (row + m) : nullptr;
+#pragma unroll
+    for (int r = 0; r < KT_R; ++r) {
+        const float gl = __ldg(pl + 32 * r);
+        const float gr = APEX ? 0.f : __ldg(pr + 32 * r);
+        if (!HASNAN) {
+            acc[r] = fmaf(w, APEX ? gl : gl + gr, acc[r]);
+            if (NEAR) {
+                const float dl = __ldg(ql + 32 * r);
+                const float dr = APEX ? 0.f : __ldg(qr + 32 * r);
+                acc[r] = fmaf(wn, APEX ? dl : dl + dr, acc[r]);
+            }
+        } else {
+            const float tl = w * gl, tr = w * gr;   // nansum: NaN terms are skipped one by one
+            if (tl == tl) acc[r] += tl;
+            if (!APEX && tr == tr) acc[r] += tr;
+            if (NEAR) {
+                const float ul = wn * __ldg(ql + 32 * r);
+                const float ur = APEX ? 0.f : wn * __ldg(qr + 32 * r);
+                if (ul == ul) acc[r] += ul;
+                if (!APEX && ur == ur) acc[r] += ur;
+            }
+        }
+        if (STATS) {
+            const int x = xbase + 32 * r;
+            if (x < p.x_end) npairs += (x - m >= 0) + (!APEX && x + m < p.T);
+        }
+    }
+}
+
+template <bool NEAR, bool HASNAN, bool STATS>
+__device__ __forceinline__ void kirch_table_loop(const KirchTabParams &p, int ti, int xbase, float (&acc)[KT_R],
+                                                 unsigned &npairs) {
+    const int n = p.nm[ti];
+    const int2 *__restrict__ trow = p.tab + (size_t)ti * p.A1;
+    const float *__restrict__ nrow = NEAR ? p.tabn + (size_t)ti * p.A1 : nullptr;
+    // lanes past the end of the profile read the zero padding (rows are over-allocated by one tile)
+    const float *__restrict__ gbase = p.gP + (p.Apad + xbase);
+    const float *__restrict__ dbase = NEAR ? p.dP + (p.Apad + xbase) : nullptr;
+    if (n > 0) {
+        const int2 e = __ldg(trow);
+        if (e.x >= 0)
+            kirch_table_step<NEAR, HASNAN, STATS, true>(p, gbase, dbase, e, NEAR ? __ldg(nrow) : 0.f, 0, xbase, acc, npairs);
+    }
+#pragma unroll 2
+    for (int m = 1; m < n; ++m) {
+        const int2 e = __ldg(trow + m);
+        if (e.x < 0) continue;  // uniform: no contribution, or ambiguous (exact fix-up pass)
+        kirch_table_step<NEAR, HASNAN, STATS, false>(p, gbase, dbase, e, NEAR ? __ldg(nrow + m) : 0.f, m, xbase, acc, npairs);
+    }
+}
+
+template <bool NEAR, bool STATS>
+__global__ void __launch_bounds__(128) kirch_table_kernel(const __grid_constant__ KirchTabParams p) {
+    const int ti = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xbase = p.x_begin + (blockIdx.y * 4 + warp) * (32 * KT_R) + lane;
+    if (xbase - lane >= p.x_end) return;
+    float acc[KT_R];
+#pragma unroll
+    for (int r = 0; r < KT_R; ++r) acc[r] = 0.f;
+    unsigned npairs = 0;
+    if (p.flags[0] != 0)
+        kirch_table_loop<NEAR, true, STATS>(p, ti, xbase, acc, npairs);
+    else
+        kirch_table_loop<NEAR, false, STATS>(p, ti, xbase, acc, npairs);
+#pragma unroll
+    for (int r = 0; r < KT_R; ++r) {
+        const int x = xbase + 32 * r;
+        if (x < p.x_end) p.out[(size_t)ti * p.ldo + (x - p.x_begin)] = acc[r];
+    }
+    if (STATS) {
+        unsigned long long np64 = npairs;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) np64 += __shfl_xor_sync(0xffffffffu, np64, o);
+        if (lane == 0 && np64) atomicAdd(&p.stats[0], np64);
+    }
+}
+
+// Exact float64 re-evaluation of every pair that uses a flagged table entry (normally none at all).
+template <bool NEAR>
+__global__ void __launch_bounds__(256) kirch_table_fixup_kernel(const __grid_constant__ KirchTabParams tp,
+                                                                const __grid_constant__ KirchParams gp) {
+    const int lane = threadIdx.x & 31;
+    const size_t nent = (size_t)tp.S * tp.A1;
+    const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t base = wid * 32; base < nent; base += nwarps * 32) {
+        const size_t ei = base + lane;
+        const bool hit = ei < nent && tp.tab[ei].x == -2;
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const size_t e = base + src;
+            const int ti = (int)(e / tp.A1), m = (int)(e % tp.A1);
+            for (int xi = tp.x_begin + lane; xi < tp.x_end; xi += 32) {
+                const double dxi = gp.dist[xi];
+                float term = 0.f;
+                if (xi - m >= 0) term += exact_term<NEAR>(gp, ti, xi - m, dxi);
+                if (m != 0 && xi + m < tp.T) term += exact_term<NEAR>(gp, ti, xi + m, dxi);
+                if (term != 0.f) {
+                    atomicAdd(&tp.out[(size_t)ti * tp.ldo + (xi - tp.x_begin)], term);
+                    if (tp.stats) atomicAdd(&tp.stats[1], 1ull);
+                }
+            }
+        }
+    }
+}
+
 static inline int kirch_sp(int S) { return ((S + 64 + 31) / 32) * 32; }
 
 static unsigned long long *g_last_stats = nullptr;
 static cudaStream_t g_last_stats_stream = nullptr;
 static int g_stats_enabled = 0;
+static int g_kirch_mode = 0;   // 0 auto, 1 general, 2 table
+static int g_last_path = 0;
 
 }  // namespace impdar
 
@@ -327,13 +561,20 @@ using namespace impdar;
 
 extern "C" {
 
+static inline size_t kirch_roundup(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
 size_t impdar_kirchhoff_workspace_bytes(int S, int T, int nearfield) {
-    const size_t sp = (size_t)kirch_sp(S);
-    size_t b = (size_t)T * sp * sizeof(float) * (nearfield ? 2 : 1);
+    const size_t nf = nearfield ? 2 : 1;
+    // general path: trace-major d/dt (and data) with padded samples and 32 spare traces
+    const size_t general = (size_t)(T + 32) * (size_t)kirch_sp(S) * sizeof(float) * nf;
+    // uniform-geometry path, worst case aperture = the whole profile: padded row-major image(s) + tables
+    const size_t tp = kirch_roundup((size_t)T + 2 * kirch_roundup((size_t)T, 32), 32);
+    const size_t table = ((size_t)S * tp + 1024) * sizeof(float) * nf + (size_t)S * (size_t)T * (sizeof(int2) + (nearfield ? 4 : 0)) +
+                         (size_t)S * sizeof(int);
+    size_t b = general > table ? general : table;
     b += 6 * (size_t)S * sizeof(double);  // zs, zs2, tt, grad coefficients
     b += (size_t)T * sizeof(double);      // dist
-    b += 256;                              // flags + stats
-    return b + 1024;
+    return b + 4096;
 }
 
 int impdar_kirchhoff_f32(const float *data, float *out, int S, int T, const double *dist_m, const double *tt_s,
@@ -374,17 +615,23 @@ int impdar_kirchhoff_f32(const float *data, float *out, int S, int T, const doub
     float thr = (float)(0.5 - delta);
     if (delta > 0.2) thr = -1.f;  // irregular sampling: everything through the exact path
 
-    // carve workspace
-    const int SP = kirch_sp(S);
+    // uniform trace spacing?  (deviation of the real positions from the fitted grid, in seconds of travel time)
+    double dxm = 0.0, maxdev_d = 0.0;
+    if (T > 1) {
+        dxm = (h_dist[T - 1] - h_dist[0]) / (double)(T - 1);
+        for (int i = 0; i < T; ++i) {
+            const double dev = fabs(h_dist[i] - (h_dist[0] + i * dxm));
+            if (dev > maxdev_d) maxdev_d = dev;
+        }
+    }
+    const double eps_t = (2.0 / vel) * (2.0 * maxdev_d) + 1e-15 * (fabs(tmax) + fabs(tt0));
+    const bool uniform_ok = monotone && T > 1 && dxm > 0.0 && tmax > 0.0 && eps_t / dt_eff < 1e-5;
+    IMPDAR_CHECK_ARG(!(g_kirch_mode == 2 && !uniform_ok), "kirchhoff: table path forced but trace spacing is not uniform");
+    const bool use_table = (g_kirch_mode == 2) || (g_kirch_mode == 0 && uniform_ok);
+
+    // carve workspace: small vectors first
     char *w = (char *)workspace;
     w = (char *)(((uintptr_t)w + 255) & ~(uintptr_t)255);
-    float *gradT = (float *)w;
-    w += (size_t)T * SP * sizeof(float);
-    float *dataT = nullptr;
-    if (nearfield) {
-        dataT = (float *)w;
-        w += (size_t)T * SP * sizeof(float);
-    }
     double *zs = (double *)w;
     w += (size_t)S * sizeof(double);
     double *zs2 = (double *)w;
@@ -395,43 +642,127 @@ int impdar_kirchhoff_f32(const float *data, float *out, int S, int T, const doub
     w += 3 * (size_t)S * sizeof(double);
     double *d_dist = (double *)w;
     w += (size_t)T * sizeof(double);
+    int *flags = (int *)w;
+    unsigned long long *stats = (unsigned long long *)(w + 64);
+    w += 256;
+    w = (char *)(((uintptr_t)w + 255) & ~(uintptr_t)255);
     IMPDAR_CUDA(cudaMemcpyAsync(d_tt, tt_s, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
     IMPDAR_CUDA(cudaMemcpyAsync(d_coef, grad_coef, 3 * (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
     IMPDAR_CUDA(cudaMemcpyAsync(d_dist, dist_m, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, st));
-    int *flags = (int *)w;
-    unsigned long long *stats = (unsigned long long *)(w + 64);
-
-    IMPDAR_CUDA(cudaMemsetAsync(gradT, 0, (size_t)T * SP * sizeof(float) * (nearfield ? 2 : 1), st));
     IMPDAR_CUDA(cudaMemsetAsync(flags, 0, 128, st));
     kirch_prep_vectors_kernel<<<(S + 255) / 256, 256, 0, st>>>(d_tt, zs, zs2, S, vel);
     IMPDAR_LAUNCH_CHECK();
-    {
-        dim3 grid((T + 31) / 32, (S + 31) / 32), block(32, 8);
-        grad_transpose_kernel<<<grid, block, 0, st>>>(data, gradT, dataT, S, T, SP, d_coef, flags);
-        IMPDAR_LAUNCH_CHECK();
-    }
+
     KirchParams p;
-    p.gradT = gradT; p.dataT = dataT; p.out = out; p.dist = d_dist; p.tt = d_tt; p.zs = zs; p.zs2 = zs2;
+    memset(&p, 0, sizeof(p));
+    p.out = out; p.dist = d_dist; p.tt = d_tt; p.zs = zs; p.zs2 = zs2;
     p.flags = flags; p.stats = stats;
-    p.S = S; p.T = T; p.SP = SP; p.ldo = x_end - x_begin; p.x_begin = x_begin; p.x_end = x_end;
+    p.S = S; p.T = T; p.ldo = x_end - x_begin; p.x_begin = x_begin; p.x_end = x_end;
     p.vel = vel; p.tmax = tmax; p.tt0 = tt0; p.inv_dt = 1.0 / dt_eff; p.cs = 2.0 / (vel * dt_eff);
     p.neg_u0 = (float)(-u0); p.thr = thr;
     p.wfar = (float)(1.0 / (2.0 * 3.14159265358979323846 * vel));
     p.wnear = (float)(4.0 / ((vel * dt_eff) * (vel * dt_eff)) / (2.0 * 3.14159265358979323846));
     p.monotone = monotone;
-    dim3 grid((S + 31) / 32, (x_end - x_begin + 7) / 8), block(32, 8);
-    if (g_stats_enabled) {
-        if (nearfield) kirch_general_kernel<true, true><<<grid, block, 0, st>>>(p);
-        else kirch_general_kernel<false, true><<<grid, block, 0, st>>>(p);
+
+    if (use_table) {
+        int Amax = (int)fmin((double)(T - 1), floor(vel * tmax / 2.0 / dxm) + 2.0);
+        if (Amax < 0) Amax = 0;
+        const int A1 = Amax + 1;
+        const int Apad = (int)kirch_roundup((size_t)Amax, 32);
+        const int Tp = (int)kirch_roundup((size_t)T + 2 * (size_t)Apad, 32);
+        const size_t img = ((size_t)S * Tp + 4 * 32 * KT_R + 32) * sizeof(float);  // + one tile of slack after the last row
+        float *gP = (float *)w;
+        w += img;
+        float *dP = nullptr;
+        if (nearfield) {
+            dP = (float *)w;
+            w += img;
+        }
+        int2 *tab = (int2 *)w;
+        w += (size_t)S * A1 * sizeof(int2);
+        float *tabn = nullptr;
+        if (nearfield) {
+            tabn = (float *)w;
+            w += (size_t)S * A1 * sizeof(float);
+        }
+        int *nm = (int *)w;
+        w += (size_t)S * sizeof(int);
+        IMPDAR_CHECK_ARG((size_t)(w - (char *)workspace) <= ws_bytes, "kirchhoff: workspace too small for the table path");
+        IMPDAR_CUDA(cudaMemsetAsync(gP, 0, img * (nearfield ? 2 : 1), st));
+        IMPDAR_CUDA(cudaMemsetAsync(nm, 0, (size_t)S * sizeof(int), st));
+        {
+            dim3 grid((A1 + 127) / 128, S);
+            kirch_table_build_kernel<<<grid, 128, 0, st>>>(tab, tabn, nm, S, A1, dxm, zs, zs2, d_tt, vel, tmax, tt0,
+                                                          1.0 / dt_eff, eps_t);
+            IMPDAR_LAUNCH_CHECK();
+        }
+        {
+            int gx = (T + 255) / 256;
+            if (gx > 64) gx = 64;
+            dim3 grid(gx, S);
+            grad_padded_kernel<<<grid, 256, 0, st>>>(data, gP, dP, S, T, Tp, Apad, d_coef, flags);
+            IMPDAR_LAUNCH_CHECK();
+        }
+        KirchTabParams tp;
+        tp.gP = gP; tp.dP = dP; tp.tab = tab; tp.tabn = tabn; tp.nm = nm; tp.out = out; tp.flags = flags;
+        tp.stats = stats; tp.S = S; tp.T = T; tp.Tp = Tp; tp.Apad = Apad; tp.A1 = A1; tp.ldo = x_end - x_begin;
+        tp.x_begin = x_begin; tp.x_end = x_end;
+        dim3 grid(S, (x_end - x_begin + 4 * 32 * KT_R - 1) / (4 * 32 * KT_R));
+        if (g_stats_enabled) {
+            if (nearfield) kirch_table_kernel<true, true><<<grid, 128, 0, st>>>(tp);
+            else kirch_table_kernel<false, true><<<grid, 128, 0, st>>>(tp);
+        } else {
+            if (nearfield) kirch_table_kernel<true, false><<<grid, 128, 0, st>>>(tp);
+            else kirch_table_kernel<false, false><<<grid, 128, 0, st>>>(tp);
+        }
+        IMPDAR_LAUNCH_CHECK();
+        // exact pass over flagged table entries (reads the same padded row-major images)
+        p.gradT = gP; p.dataT = dP; p.rowmajor = 1; p.Tp = Tp; p.Apad = Apad;
+        if (nearfield) kirch_table_fixup_kernel<true><<<num_sms() * 2, 256, 0, st>>>(tp, p);
+        else kirch_table_fixup_kernel<false><<<num_sms() * 2, 256, 0, st>>>(tp, p);
+        IMPDAR_LAUNCH_CHECK();
     } else {
-        if (nearfield) kirch_general_kernel<true, false><<<grid, block, 0, st>>>(p);
-        else kirch_general_kernel<false, false><<<grid, block, 0, st>>>(p);
+        IMPDAR_CHECK_ARG((unsigned long long)(T + 32) * (unsigned long long)kirch_sp(S) < (1ull << 32),
+                         "kirchhoff: (tnum + 32) * padded snum must stay below 2^32 elements");
+        const int SP = kirch_sp(S);
+        const size_t tbytes = (size_t)(T + 32) * SP * sizeof(float);  // 32 zero rows: chunks are padded to 4 traces
+        float *gradT = (float *)w;
+        w += tbytes;
+        float *dataT = nullptr;
+        if (nearfield) {
+            dataT = (float *)w;
+            w += tbytes;
+        }
+        IMPDAR_CUDA(cudaMemsetAsync(gradT, 0, tbytes * (nearfield ? 2 : 1), st));
+        {
+            dim3 grid((T + 31) / 32, (S + 31) / 32), block(32, 8);
+            grad_transpose_kernel<<<grid, block, 0, st>>>(data, gradT, dataT, S, T, SP, d_coef, flags);
+            IMPDAR_LAUNCH_CHECK();
+        }
+        p.gradT = gradT; p.dataT = dataT; p.SP = SP;
+        dim3 grid((S + 31) / 32, (x_end - x_begin + 7) / 8), block(32, 8);
+        if (g_stats_enabled) {
+            if (nearfield) kirch_general_kernel<true, true><<<grid, block, 0, st>>>(p);
+            else kirch_general_kernel<false, true><<<grid, block, 0, st>>>(p);
+        } else {
+            if (nearfield) kirch_general_kernel<true, false><<<grid, block, 0, st>>>(p);
+            else kirch_general_kernel<false, false><<<grid, block, 0, st>>>(p);
+        }
+        IMPDAR_LAUNCH_CHECK();
     }
-    IMPDAR_LAUNCH_CHECK();
     g_last_stats = stats;
     g_last_stats_stream = st;
+    g_last_path = use_table ? 2 : 1;
     return IMPDAR_B200_OK;
 }
+
+int impdar_kirchhoff_set_mode(int mode) {
+    IMPDAR_CHECK_ARG(mode >= 0 && mode <= 2, "kirchhoff_set_mode: 0 auto, 1 general kernel, 2 uniform-geometry table kernel");
+    g_kirch_mode = mode;
+    return IMPDAR_B200_OK;
+}
+
+int impdar_kirchhoff_last_path(void) { return g_last_path; }
 
 int impdar_kirchhoff_enable_stats(int on) {
     g_stats_enabled = on ? 1 : 0;

@@ -125,6 +125,20 @@ def enable_kirchhoff_stats(on=True):
     _lib.check(_lib.load().impdar_kirchhoff_enable_stats(int(bool(on))))
 
 
+KIRCHHOFF_AUTO, KIRCHHOFF_GENERAL, KIRCHHOFF_TABLE = 0, 1, 2
+
+
+def set_kirchhoff_mode(mode=KIRCHHOFF_AUTO):
+    """Kernel selection: AUTO picks the uniform-geometry table kernel when the trace spacing is uniform and the
+    general-geometry kernel otherwise; GENERAL / TABLE force one (TABLE raises ValueError on irregular spacing)."""
+    _lib.check(_lib.load().impdar_kirchhoff_set_mode(int(mode)))
+
+
+def kirchhoff_last_path():
+    """'general' or 'table': which kernel the last Kirchhoff call ran."""
+    return {1: 'general', 2: 'table'}.get(_lib.load().impdar_kirchhoff_last_path(), 'none')
+
+
 # -------------------------------------------------------------------------------------------- Stolt
 def stolt_device(data_dev, dt, dx, vel, htaper, vtaper, trunc_int=False, out=None):
     """(batch, snum, tnum) or (snum, tnum) float32 CUDA tensor -> migrated (.., 2*(snum//2), tnum)."""

@@ -102,6 +102,11 @@ int impdar_kirchhoff_f32(const float *data, float *out, int snum, int tnum, cons
  * inside the aperture and pairs that took the float64 exact path.  Counting pairs costs an instruction
  * per pair, so it is off unless enabled.  last_stats synchronises the stream of that call.            */
 int impdar_kirchhoff_enable_stats(int on);
+/* Kernel selection: 0 = automatic (uniform-geometry table kernel when the trace spacing is uniform, the
+ * general-geometry kernel otherwise), 1 = always the general kernel, 2 = require the table kernel.
+ * impdar_kirchhoff_last_path() tells which one the last call used (1 general, 2 table).              */
+int impdar_kirchhoff_set_mode(int mode);
+int impdar_kirchhoff_last_path(void);
 int impdar_kirchhoff_last_stats(unsigned long long *pairs, unsigned long long *exact_pairs);
 
 /* Reference prototype, migrationlib/mig_cython.h:11 - HOST pointers, float64, synchronous.  Linking

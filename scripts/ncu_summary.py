@@ -1,0 +1,24 @@
+"""Print the handful of ncu metrics we track from a --page raw --csv export (one row per kernel)."""
+import csv, sys
+rows = list(csv.reader(open(sys.argv[1])))
+hdr, units = rows[0], rows[1]
+keys = ['Kernel Name', 'gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum', 'l1tex__t_sector_hit_rate.pct',
+        'smsp__inst_executed.sum', 'sm__inst_executed_pipe_fma.sum', 'sm__inst_executed_pipe_alu.sum',
+        'sm__inst_executed_pipe_xu.sum', 'sm__inst_executed_pipe_lsu.sum', 'sm__inst_executed_pipe_fp64.sum',
+        'sm__inst_executed_pipe_uniform.sum', 'smsp__thread_inst_executed_per_inst_executed.ratio',
+        'l1tex__data_pipe_lsu_wavefronts.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']
+for vals in rows[2:]:
+    print('-' * 100)
+    for i, h in enumerate(hdr):
+        if h in keys or (h.startswith('smsp__warp_issue_stalled') and h.endswith('per_warp_active.pct')) \
+                or h.startswith('smsp__average_warps_issue_stalled') and h.endswith('_per_issue_active.ratio'):
+            try:
+                v = float(vals[i].replace(',', ''))
+                if h.startswith('smsp__warp_issue_stalled') and v < 2.0:
+                    continue
+            except ValueError:
+                pass
+            print(f'{h:85s} {vals[i]:>20s} {units[i]}')
