@@ -372,7 +372,8 @@ __global__ void __launch_bounds__(128) kirch_table_build_kernel(int2 *__restrict
                                                                 const double *__restrict__ zs,
                                                                 const double *__restrict__ zs2,
                                                                 const double *__restrict__ tt, double vel, double tmax,
-                                                                double tt0, double inv_dt, double eps_t) {
+                                                                double tt0, double inv_dt, double eps_t,
+                                                                int *__restrict__ amb_list, int *__restrict__ amb_count) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     const int ti = blockIdx.y;
     if (m >= A1) return;
@@ -403,6 +404,7 @@ __global__ void __launch_bounds__(128) kirch_table_build_kernel(int2 *__restrict
     tab[(size_t)ti * A1 + m] = make_int2(k, __float_as_int(w));
     if (tabn) tabn[(size_t)ti * A1 + m] = wn;
     if (k != -1) atomicMax(&nm[ti], m + 1);
+    if (k == -2) amb_list[atomicAdd(amb_count, 1)] = ti * A1 + m;  // list has room for every entry
 }
 
 // d/dt (np.gradient stencil) into the padded row-major layout; also the non-finite scan.
@@ -516,34 +518,29 @@ __global__ void __launch_bounds__(128) kirch_table_kernel(const __grid_constant_
     }
 }
 
-// Exact float64 re-evaluation of every pair that uses a flagged table entry (normally none at all).
+// Exact float64 re-evaluation of every pair that uses a flagged table entry (normally a handful: the apex of
+// the last sample sits exactly on the aperture cut).  Work item = (flagged entry, block of 32 output traces).
 template <bool NEAR>
 __global__ void __launch_bounds__(256) kirch_table_fixup_kernel(const __grid_constant__ KirchTabParams tp,
-                                                                const __grid_constant__ KirchParams gp) {
+                                                                const __grid_constant__ KirchParams gp,
+                                                                const int *__restrict__ amb_list,
+                                                                const int *__restrict__ amb_count) {
     const int lane = threadIdx.x & 31;
-    const size_t nent = (size_t)tp.S * tp.A1;
-    const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t base = wid * 32; base < nent; base += nwarps * 32) {
-        const size_t ei = base + lane;
-        const bool hit = ei < nent && tp.tab[ei].x == -2;
-        unsigned mask = __ballot_sync(0xffffffffu, hit);
-        while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const size_t e = base + src;
-            const int ti = (int)(e / tp.A1), m = (int)(e % tp.A1);
-            for (int xi = tp.x_begin + lane; xi < tp.x_end; xi += 32) {
-                const double dxi = gp.dist[xi];
-                float term = 0.f;
-                if (xi - m >= 0) term += exact_term<NEAR>(gp, ti, xi - m, dxi);
-                if (m != 0 && xi + m < tp.T) term += exact_term<NEAR>(gp, ti, xi + m, dxi);
-                if (term != 0.f) {
-                    atomicAdd(&tp.out[(size_t)ti * tp.ldo + (xi - tp.x_begin)], term);
-                    if (tp.stats) atomicAdd(&tp.stats[1], 1ull);
-                }
-            }
-        }
+    const long long nblk = (tp.x_end - tp.x_begin + 31) / 32;
+    const long long nitems = (long long)(*amb_count) * nblk;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long it = wid; it < nitems; it += nwarps) {
+        const int e = amb_list[it / nblk];
+        const int ti = e / tp.A1, m = e % tp.A1;
+        const int xi = tp.x_begin + (int)(it % nblk) * 32 + lane;
+        if (xi >= tp.x_end) continue;
+        const double dxi = gp.dist[xi];
+        float term = 0.f;
+        if (xi - m >= 0) term += exact_term<NEAR>(gp, ti, xi - m, dxi);
+        if (m != 0 && xi + m < tp.T) term += exact_term<NEAR>(gp, ti, xi + m, dxi);
+        if (term != 0.f) atomicAdd(&tp.out[(size_t)ti * tp.ldo + (xi - tp.x_begin)], term);
+        if (tp.stats) atomicAdd(&tp.stats[1], 1ull);
     }
 }
 
@@ -569,7 +566,7 @@ size_t impdar_kirchhoff_workspace_bytes(int S, int T, int nearfield) {
     const size_t general = (size_t)(T + 32) * (size_t)kirch_sp(S) * sizeof(float) * nf;
     // uniform-geometry path, worst case aperture = the whole profile: padded row-major image(s) + tables
     const size_t tp = kirch_roundup((size_t)T + 2 * kirch_roundup((size_t)T, 32), 32);
-    const size_t table = ((size_t)S * tp + 1024) * sizeof(float) * nf + (size_t)S * (size_t)T * (sizeof(int2) + (nearfield ? 4 : 0)) +
+    const size_t table = ((size_t)S * tp + 1024) * sizeof(float) * nf + (size_t)S * (size_t)T * (sizeof(int2) + sizeof(int) + (nearfield ? 4 : 0)) +
                          (size_t)S * sizeof(int);
     size_t b = general > table ? general : table;
     b += 6 * (size_t)S * sizeof(double);  // zs, zs2, tt, grad coefficients
@@ -687,13 +684,17 @@ int impdar_kirchhoff_f32(const float *data, float *out, int S, int T, const doub
         }
         int *nm = (int *)w;
         w += (size_t)S * sizeof(int);
+        int *amb_list = (int *)w;
+        w += (size_t)S * A1 * sizeof(int);
+        int *amb_count = flags + 8;
+        IMPDAR_CHECK_ARG((unsigned long long)S * (unsigned long long)A1 < (1ull << 31), "kirchhoff: table too large");
         IMPDAR_CHECK_ARG((size_t)(w - (char *)workspace) <= ws_bytes, "kirchhoff: workspace too small for the table path");
         IMPDAR_CUDA(cudaMemsetAsync(gP, 0, img * (nearfield ? 2 : 1), st));
         IMPDAR_CUDA(cudaMemsetAsync(nm, 0, (size_t)S * sizeof(int), st));
         {
             dim3 grid((A1 + 127) / 128, S);
             kirch_table_build_kernel<<<grid, 128, 0, st>>>(tab, tabn, nm, S, A1, dxm, zs, zs2, d_tt, vel, tmax, tt0,
-                                                          1.0 / dt_eff, eps_t);
+                                                          1.0 / dt_eff, eps_t, amb_list, amb_count);
             IMPDAR_LAUNCH_CHECK();
         }
         {
@@ -718,8 +719,8 @@ int impdar_kirchhoff_f32(const float *data, float *out, int S, int T, const doub
         IMPDAR_LAUNCH_CHECK();
         // exact pass over flagged table entries (reads the same padded row-major images)
         p.gradT = gP; p.dataT = dP; p.rowmajor = 1; p.Tp = Tp; p.Apad = Apad;
-        if (nearfield) kirch_table_fixup_kernel<true><<<num_sms() * 2, 256, 0, st>>>(tp, p);
-        else kirch_table_fixup_kernel<false><<<num_sms() * 2, 256, 0, st>>>(tp, p);
+        if (nearfield) kirch_table_fixup_kernel<true><<<num_sms() * 2, 256, 0, st>>>(tp, p, amb_list, amb_count);
+        else kirch_table_fixup_kernel<false><<<num_sms() * 2, 256, 0, st>>>(tp, p, amb_list, amb_count);
         IMPDAR_LAUNCH_CHECK();
     } else {
         IMPDAR_CHECK_ARG((unsigned long long)(T + 32) * (unsigned long long)kirch_sp(S) < (1ull << 32),

@@ -55,3 +55,17 @@ if 'phsh' in which:
         vm=np.linspace(1.69e8,2.2e8,S)
         ms=ev(lambda: ml.phase_shift_device(x,1e-8,5.0,tt,vm,10,10),n=2)
         print(f'phsh layered {S}x{T}: {ms:.2f} ms  {S*T/ms*1e3:.3e} samples/s',flush=True)
+if 'kmodes' in which:
+    for (S,T) in [(2048,4096),(8192,16384)]:
+        x=torch.randn(S,T,device='cuda'); tt,dist=geom(S,T)
+        for mode,name in ((1,'general'),(2,'table')):
+            ml.set_kirchhoff_mode(mode)
+            ml.enable_kirchhoff_stats(True)
+            ml.kirchhoff_device(x,tt,dist,1.69e8,False); torch.cuda.synchronize()
+            pairs,exact=ml.kirchhoff_stats()
+            ml.enable_kirchhoff_stats(False)
+            ms=ev(lambda: ml.kirchhoff_device(x,tt,dist,1.69e8,False))
+            print(f'kirch[{name}] {S}x{T}: {ms:.2f} ms  {S*T/ms*1e3:.3e} samples/s  pairs {pairs:.3e} exact {exact:.3e} {pairs/ms*1e3:.3e} pairs/s',flush=True)
+            ms=ev(lambda: ml.kirchhoff_device(x,tt,dist,1.69e8,True))
+            print(f'kirch[{name}] near {S}x{T}: {ms:.2f} ms',flush=True)
+        ml.set_kirchhoff_mode(0)
