@@ -7,6 +7,13 @@
 //   1 taper (fp32, vectorised)            2 cuFFT R2C along time (stride = tnum, batch = tnum)
 //   3 cuFFT C2C along traces, in place    4 remap + obliquity + 1/(S'T) scale kernel (this file)
 //   5 cuFFT C2C inverse along traces      6 cuFFT C2R along time
+// Even snum and tnum take the paired-trace pipeline instead (three sweeps fewer, no real-transform wrappers):
+//   adjacent traces are one complex signal z[s][j] = d[s][2j] + i d[s][2j+1] (a reinterpretation of the same
+//   memory), transformed by plain in-place 2-D C2C FFTs; stolt_remap_paired_kernel recovers
+//   FK[w][kx] = E[w][kx mod T/2] + e^{-2 pi i kx/T} O[w][kx mod T/2] from Zh = E + iO and its Hermitian partner
+//   Zh[-w][-k] on the fly, applies the remap to the two columns kx and kx + T/2, and writes the spectrum of the
+//   output image in the same paired form (plus its Hermitian mirror row), so the inverse C2C lands the real
+//   result directly in the output layout.
 // The remap coordinate f = w'/dw = sqrt(j^2 + beta^2) is evaluated in fp64 (f reaches ~snum/2 and the
 // interpolation weight is its fractional part); the interpolation itself is fp32 complex FMA.
 #include <cufft.h>
@@ -77,17 +84,115 @@ __global__ void __launch_bounds__(128) stolt_remap_kernel(const __grid_constant_
     }
 }
 
+
+struct StoltPairedParams {
+    const float2 *Zh;  // (S, Th) forward 2-D spectrum of the paired image
+    float2 *Zq;        // (S, Th) spectrum of the paired output image
+    int S, Th, T, nz;
+    double beta_unit;
+    float norm;        // 1 / (S * T)
+};
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// FK[i][kap] and FK[i][kap + Th] from the paired spectrum: E = (Z + conj(Zp))/2, O = (Z - conj(Zp))/(2i),
+// FK = E +- w O with w = exp(-2 pi i kap / T).
+__device__ __forceinline__ void paired_row(const StoltPairedParams &p, int i, int kap, int kapm, float2 w, float2 &fa,
+                                           float2 &fb) {
+    const float2 z = p.Zh[(size_t)i * p.Th + kap];
+    const int im = (i == 0) ? 0 : p.S - i;
+    const float2 zp = p.Zh[(size_t)im * p.Th + kapm];
+    const float2 e = make_float2(0.5f * (z.x + zp.x), 0.5f * (z.y - zp.y));
+    const float2 o = make_float2(0.5f * (z.y + zp.y), -0.5f * (z.x - zp.x));
+    const float2 wo = cmul(w, o);
+    fa = cadd(e, wo);
+    fb = csub(e, wo);
+}
+
+__global__ void __launch_bounds__(128) stolt_remap_paired_kernel(const __grid_constant__ StoltPairedParams p,
+                                                                 int rows_per_cta) {
+    const int kap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kap >= p.Th) return;
+    const int kapm = (kap == 0) ? 0 : p.Th - kap;
+    double sn, cs;
+    sincospi(-2.0 * (double)kap / (double)p.T, &sn, &cs);
+    const float2 w = make_float2((float)cs, (float)sn);
+    const float2 wc = make_float2(w.x, -w.y);
+    const double betaA = p.beta_unit * (double)kap, betaB = p.beta_unit * (double)(p.Th - kap);
+    const double bA2 = betaA * betaA, bB2 = betaB * betaB;
+    const double fmax = (double)p.nz;  // last rfft row index M - 1 = S/2
+    const int j0 = blockIdx.y * rows_per_cta;
+    const int j1 = min(p.nz, j0 + rows_per_cta);
+    int curA = -2, curB = -2;
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0, tmp;
+    for (int j = j0; j < j1; ++j) {
+        if (j == 0) {  // kz = 0 row: scaling is 0 (and KK[0,0] = 0); its mirror is itself; also clear the Nyquist row
+            p.Zq[kap] = make_float2(0.f, 0.f);
+            p.Zq[(size_t)p.nz * p.Th + kap] = make_float2(0.f, 0.f);
+            continue;
+        }
+        const double jj = (double)j * (double)j;
+        // ---- column kx = kap
+        const double fA = sqrt(jj + bA2);
+        {
+            const double fq = fmin(fA, fmax);
+            const int i0 = min((int)fq, p.nz - 1);
+            if (i0 != curA) {
+                if (i0 == curA + 1) a0 = a1; else paired_row(p, i0, kap, kapm, w, a0, tmp);
+                paired_row(p, i0 + 1, kap, kapm, w, a1, tmp);
+                curA = i0;
+            }
+        }
+        const double fqA = fmin(fA, fmax);
+        const float aA = (float)(fqA - (double)curA);
+        const float scA = (float)((double)j / fA) * p.norm;
+        const float2 gA = make_float2(fmaf(a0.x, (1.f - aA) * scA, a1.x * (aA * scA)),
+                                      fmaf(a0.y, (1.f - aA) * scA, a1.y * (aA * scA)));
+        // ---- column kx = kap + Th
+        const double fB = sqrt(jj + bB2);
+        {
+            const double fq = fmin(fB, fmax);
+            const int i0 = min((int)fq, p.nz - 1);
+            if (i0 != curB) {
+                if (i0 == curB + 1) b0 = b1; else paired_row(p, i0, kap, kapm, w, tmp, b0);
+                paired_row(p, i0 + 1, kap, kapm, w, tmp, b1);
+                curB = i0;
+            }
+        }
+        const double fqB = fmin(fB, fmax);
+        const float aB = (float)(fqB - (double)curB);
+        const float scB = (float)((double)j / fB) * p.norm;
+        const float2 gB = make_float2(fmaf(b0.x, (1.f - aB) * scB, b1.x * (aB * scB)),
+                                      fmaf(b0.y, (1.f - aB) * scB, b1.y * (aB * scB)));
+        // ---- paired output spectrum and its Hermitian mirror
+        const float2 e = cadd(gA, gB);
+        const float2 o = cmul(csub(gA, gB), wc);
+        p.Zq[(size_t)j * p.Th + kap] = make_float2(e.x - o.y, e.y + o.x);              // E' + i O'
+        p.Zq[(size_t)(p.S - j) * p.Th + kapm] = make_float2(e.x + o.y, o.x - e.y);     // conj(E') + i conj(O')
+    }
+}
+
 struct StoltPlans {
-    cufftHandle r2c = 0, c2c = 0, c2r = 0;
+    cufftHandle r2c = 0, c2c = 0, c2r = 0, c2c2d = 0;
+    bool paired = false;
 };
 static std::map<std::tuple<int, int, int>, StoltPlans> g_plans;  // (device, S, T)
 static std::mutex g_plans_mu;
+
+static int g_stolt_force_r2c = 0;
+static inline bool stolt_use_paired(int S, int T) {
+    return !g_stolt_force_r2c && (S % 2 == 0) && (T % 2 == 0) && S >= 4 && T >= 4;
+}
 
 static int get_plans(int S, int T, StoltPlans &out) {
     int dev = 0;
     IMPDAR_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_plans_mu);
-    auto key = std::make_tuple(dev, S, T);
+    auto key = std::make_tuple(dev, S, stolt_use_paired(S, T) ? T : -T);
     auto it = g_plans.find(key);
     if (it != g_plans.end()) {
         out = it->second;
@@ -96,6 +201,14 @@ static int get_plans(int S, int T, StoltPlans &out) {
     StoltPlans pl;
     const int M = S / 2 + 1;
     const int S2 = 2 * (M - 1);
+    pl.paired = stolt_use_paired(S, T);
+    if (pl.paired) {
+        int n[2] = {S, T / 2};
+        IMPDAR_CUFFT(cufftPlanMany(&pl.c2c2d, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2C, 1));
+        g_plans[key] = pl;
+        out = pl;
+        return IMPDAR_B200_OK;
+    }
     {
         int n[1] = {S}, inembed[1] = {S}, onembed[1] = {M};
         IMPDAR_CUFFT(cufftPlanMany(&pl.r2c, 1, n, inembed, T, 1, onembed, T, 1, CUFFT_R2C, T));
@@ -149,6 +262,29 @@ int impdar_stolt_f32(const float *data, float *out, int S, int T, int batch, dou
     StoltPlans pl;
     int rc = get_plans(S, T, pl);
     if (rc) return rc;
+    if (pl.paired) {
+        IMPDAR_CUFFT(cufftSetStream(pl.c2c2d, st));
+        StoltPairedParams pp;
+        pp.S = S; pp.Th = T / 2; pp.T = T; pp.nz = S / 2;
+        pp.beta_unit = vel * (double)S * dt / (2.0 * (double)T * dx);
+        pp.norm = (float)(1.0 / ((double)S * (double)T));
+        for (int b = 0; b < batch; ++b) {
+            const float *din = data + (size_t)b * S * T;
+            float *dout = out + (size_t)b * S * T;
+            rc = impdar_taper_f32(din, bufA, S, T, 1, htaper, vtaper, trunc_int, stream);
+            if (rc) return rc;
+            IMPDAR_CUFFT(cufftExecC2C(pl.c2c2d, (cufftComplex *)bufA, (cufftComplex *)bufA, CUFFT_FORWARD));
+            pp.Zh = (const float2 *)bufA;
+            pp.Zq = (float2 *)dout;
+            const int rows_per_cta = 32;
+            dim3 grid((pp.Th + 127) / 128, (pp.nz + rows_per_cta - 1) / rows_per_cta);
+            stolt_remap_paired_kernel<<<grid, 128, 0, st>>>(pp, rows_per_cta);
+            IMPDAR_LAUNCH_CHECK();
+            IMPDAR_CUFFT(cufftExecC2C(pl.c2c2d, (cufftComplex *)dout, (cufftComplex *)dout, CUFFT_INVERSE));
+            count_launch(2);
+        }
+        return IMPDAR_B200_OK;
+    }
     IMPDAR_CUFFT(cufftSetStream(pl.r2c, st));
     IMPDAR_CUFFT(cufftSetStream(pl.c2c, st));
     IMPDAR_CUFFT(cufftSetStream(pl.c2r, st));
@@ -177,6 +313,12 @@ int impdar_stolt_f32(const float *data, float *out, int S, int T, int batch, dou
         IMPDAR_CUFFT(cufftExecC2R(pl.c2r, (cufftComplex *)bufKK, dout));
         count_launch(2);
     }
+    return IMPDAR_B200_OK;
+}
+
+/* Testing hook: 1 forces the generic R2C/C2R pipeline even when the paired-trace one applies. */
+int impdar_stolt_force_r2c(int on) {
+    g_stolt_force_r2c = on ? 1 : 0;
     return IMPDAR_B200_OK;
 }
 

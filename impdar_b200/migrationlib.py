@@ -158,6 +158,11 @@ def stolt_device(data_dev, dt, dx, vel, htaper, vtaper, trunc_int=False, out=Non
     return out[0] if squeeze else out
 
 
+def stolt_force_generic(on=True):
+    """Testing hook: force the generic R2C/C2R Stolt pipeline even where the paired-trace C2C pipeline applies."""
+    _lib.check(_lib.load().impdar_stolt_force_r2c(int(bool(on))))
+
+
 def migrationStolt(dat, vel=1.68e8, htaper=100, vtaper=1000):
     """Stolt f-k migration; mirrors mig_python.py:126-208 (output has 2*(snum//2) rows, :202)."""
     print('Stolt Migration (f-k migration) of %.0fx%.0f matrix' % (dat.snum, dat.tnum))

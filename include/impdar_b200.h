@@ -126,6 +126,10 @@ int impdar_stolt_f32(const float *data, float *out, int snum, int tnum, int batc
                      double vel, double htaper, double vtaper, int trunc_int, void *workspace,
                      size_t workspace_bytes, void *stream);
 
+/* Testing hook: 1 forces the generic R2C/C2R pipeline even where the paired-trace C2C pipeline (even snum and
+ * tnum) applies; 0 restores automatic selection.                                                      */
+int impdar_stolt_force_r2c(int on);
+
 /* -------------------------------------- phase shift (mig_python.py:211-287, 361-493) --- */
 /* data (snum, tnum) -> out (snum, tnum).  vmig == NULL: constant velocity `vel` (:396-420);
  * otherwise vmig: device, snum doubles, the layered profile from getVelocityProfile (:439-487) and

@@ -68,11 +68,19 @@ def test_kirchhoff_vs_oracle(S, T, tt0, nearfield, mode):
     assert _report("kirch %dx%d %s" % (S, T, mode), got.cpu().numpy(), want) < TOL
 
 
+@pytest.mark.parametrize("pipeline", ["auto", "generic"])
 @pytest.mark.parametrize("name", golden_names(contains="_stolt"))
-def test_stolt_golden(name):
+def test_stolt_golden(name, pipeline):
+    """auto = paired-trace C2C pipeline for even shapes; generic = R2C/C2R pipeline (odd shapes always use it)."""
+    from impdar_b200 import migrationlib as ml
     g = load_golden(name)
     d = dat_from_golden(g)
-    d.migrate(mtype='stolt', vel=float(g["vel"]), htaper=float(g["htaper"]), vtaper=float(g["vtaper"]))
+    ml.stolt_force_generic(pipeline == "generic")
+    try:
+        d.migrate(mtype='stolt', vel=float(g["vel"]), htaper=float(g["htaper"]), vtaper=float(g["vtaper"]))
+    finally:
+        ml.stolt_force_generic(False)
+    name = name + "[" + pipeline + "]"
     assert d.data.shape == g["out"].shape
     assert d.data.dtype == (np.float32 if g["data"].dtype == np.float32 else np.float64)
     assert _report(name, d.data, g["out"]) < TOL
@@ -138,6 +146,17 @@ def test_vbp_golden(name):
     d32.vertical_band_pass(float(g["low"]), float(g["high"]), order=int(g["order"]), filttype=str(g["filttype"]))
     assert d32.data.dtype == np.float32
     assert _report(name + "[f32]", d32.data, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("S,T", [(512, 768), (500, 1026), (333, 200)])
+def test_stolt_vs_oracle(S, T):
+    from oracle import migration as om
+    d = synthetic_dat(S, T, seed=S * 3 + T)
+    x64 = d.data.astype(np.float64)
+    _, want = om.stolt(x64, d.dt, d.trace_int, d.dist, 1.68e8, 10, 20)
+    d.migrate(mtype='stolt', vel=1.68e8, htaper=10, vtaper=20)
+    assert d.data.shape == want.shape and d.data.dtype == np.float32
+    assert _report("stolt %dx%d" % (S, T), d.data, want) < TOL
 
 
 def test_noinit_fixtures():
