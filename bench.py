@@ -146,12 +146,22 @@ class KirchhoffC2(Workload):
         return self.S * self.T * 4, d.data.nbytes, float(d.data[self.S // 2, self.T // 2])
 
     def roofline(self, ms, hbm_gbs, src):
-        # not HBM-bound; unit of work = one (output sample, in-aperture input trace) pair,
-        # issue ceiling ~4.0e12 pairs/s/GPU; the compulsory HBM traffic (8 B/sample) is reported beside it.
+        # Kirchhoff is not HBM-bound.  Unit of work = one (output sample, in-aperture input trace)
+        # pair.  The uniform-geometry table kernel issues exactly one 4-byte L1 load per pair as contiguous
+        # (generally misaligned -> two wavefronts) 128-byte warp loads, so its bound is the L1 load path:
+        # 148 SM x 32 lanes x 1.965 GHz / 2 = 4.65e12 pair/s.  SURVEY's issue-model ceiling (4.0e12) and the
+        # compulsory HBM traffic (8 B/sample) are reported beside it.
+        from impdar_b200 import migrationlib as ml
+        path = ml.kirchhoff_last_path()
         pairs_s = self.pairs / (ms * 1e-3)
         hbm = self.units * 8 / (ms * 1e-3) / 1e9
-        return {"bound": "sm_issue", "achieved": pairs_s, "peak": 4.0e12, "unit": "pair/s",
-                "frac": pairs_s / 4.0e12, "traffic": None, "kernel": "kirch_general_kernel (+ gradient/transpose pre-pass)",
+        peak = 148 * 32 * 1.965e9 / 2.0 if path == "table" else 148 * 128 * 1.965e9 / 18.0
+        return {"bound": "l1_load_wavefronts" if path == "table" else "sm_issue", "achieved": pairs_s, "peak": peak,
+                "unit": "pair/s", "frac": pairs_s / peak, "traffic": None,
+                "kernel": "kirch_table_kernel" if path == "table" else "kirch_general_kernel",
+                "peak_model": ("one misaligned 128B L1 load per 32 pairs = 2 wavefronts/SM/clk" if path == "table"
+                               else "18 issue slots per pair (measured SASS: 23)"),
+                "survey_issue_model_peak": 4.0e12, "frac_of_survey_model": pairs_s / 4.0e12,
                 "pairs_per_launch": self.pairs, "exact_fp64_pairs": self.exact_pairs,
                 "hbm_compulsory_gbs": hbm, "hbm_frac_of_%s_peak" % src: hbm / hbm_gbs}
 
@@ -244,13 +254,14 @@ class StoltC5(Workload):
     def roofline(self, ms, hbm_gbs, src):
         gbs = self.units * 40 / (ms * 1e-3) / 1e9   # 40 B per real sample, five sweeps
         return {"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs,
-                "traffic": None, "kernel": "whole Stolt step: taper + 4 cuFFT passes + stolt_remap_kernel",
+                "traffic": None, "kernel": "whole Stolt step: taper + 2-D C2C (cuFFT) + stolt_remap_paired_kernel + 2-D C2C",
                 "bytes_per_sample": 40, "compulsory_8B_gbs": self.units * 8 / (ms * 1e-3) / 1e9}
 
     def cpu_sample(self, n, xi=None):
         from oracle import migration as om
         S, T = 512, 1024   # bounded sample: same per-cell cost (two FITPACK point evaluations per (kz, kx) cell)
-        x64 = self.x[:S, :T].double().cpu().numpy()
+        img = self.x if self.x.dim() == 2 else self.x[0]
+        x64 = img[:S, :T].double().cpu().numpy()
         t0 = time.perf_counter()
         om.stolt_loops(x64, 1e-8, np.ones(T) * 5.0, np.arange(T) * 0.005, VEL_S, 10, 10, row_stride=max(1, 256 // n))
         return time.perf_counter() - t0, S * T * n / 256.0
@@ -323,9 +334,11 @@ class PipelineC4(Workload):
         of.horizontalfilt(y, self.tt, 0, self.T)
         t_f = time.perf_counter() - t0
         t_s, cells = StoltC5.cpu_sample(self, n)
-        # Stolt cost scales with cells; extrapolate it to one full profile and add the measured filters
+        # Stolt cost scales with cells: extrapolate it to one full profile, add the measured filters, and report
+        # the measured time with the equivalent number of fully processed samples
         t_full = t_f + t_s * (self.S * self.T) / cells
-        return t_full, self.S * self.T
+        elapsed = t_f + t_s
+        return elapsed, self.S * self.T * elapsed / t_full
 
     cpu_sample_desc = ("oracle vertical_band_pass + horizontalfilt on one full profile (measured) + stolt_loops on %d/256 "
                        "of the rows of a 512x1024 crop extrapolated by cell count to the profile")
@@ -416,6 +429,14 @@ class _quiet(object):
 
 
 # ------------------------------------------------------------------------------------- reference arm
+_REF_WL = None
+
+
+def _ref_job(xi):
+    wl, n = _REF_WL
+    return wl.cpu_sample(n, xi)
+
+
 def cpu_only_setup(wl):
     """Build the workload's synthetic input on the host (no CUDA) for the CPU arms."""
     from impdar_b200 import synthetic
@@ -443,7 +464,6 @@ def run_reference(args, rank, world):
     """The reference's CPU implementation of the path (the oracle's reference-cost port) on all host cores."""
     if rank != 0:
         return
-    import concurrent.futures as cf
     import torch
     cores = os.cpu_count() or 1
     wl = WORKLOADS[args.workload](args, 0, 1)
@@ -451,15 +471,15 @@ def run_reference(args, rank, world):
     n = max(1, wl.cpu_default_n // 4)
     torch.set_num_threads(1)
 
+    import multiprocessing as mp
+    global _REF_WL
+    _REF_WL = (wl, n)
+    pool = mp.get_context("fork").Pool(cores)   # the reference is single-threaded Python: one process per core
+
     def one_step():
         t0 = time.perf_counter()
-        units = 0.0
-        with cf.ThreadPoolExecutor(max_workers=cores) as ex:   # numpy releases the GIL in the heavy calls
-            futs = [ex.submit(wl.cpu_sample, n, (wl.T // 2 + 7 * i) % wl.T) for i in range(cores)]
-            for f in futs:
-                _, u = f.result()
-                units += u
-        return time.perf_counter() - t0, units
+        res = pool.map(_ref_job, [(wl.T // 2 + 7 * i) % wl.T for i in range(cores)])
+        return time.perf_counter() - t0, float(sum(u for _, u in res))
 
     for _ in range(min(args.warmup, 1)):
         one_step()
@@ -474,7 +494,7 @@ def run_reference(args, rank, world):
             "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl.name},
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": (wl.cpu_sample_desc % n) + "; %d concurrent samples (threads), one per core" % cores},
+                             "sample": (wl.cpu_sample_desc % n) + "; %d concurrent samples (processes), one per core" % cores},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
