@@ -292,7 +292,8 @@ template <typename T, int NS>
 static int launch_filtfilt(const T *x, T *y, T *work, int S, int Tn, int batch, int padlen, const IirCoef &c,
                            cudaStream_t st) {
     const long long ntraces = (long long)batch * Tn;
-    const int block = 64;
+    // one trace per thread: small problems use one warp per CTA so that every SM gets work
+    const int block = (ntraces < (long long)num_sms() * 64 * 2) ? 32 : 64;
     const long long grid = (ntraces + block - 1) / block;
     filtfilt_kernel<T, NS><<<(unsigned)grid, block, 0, st>>>(x, y, work, S, Tn, ntraces, padlen, c);
     IMPDAR_LAUNCH_CHECK();

@@ -77,13 +77,22 @@ def free_workspaces():
 
 
 def to_host(t, np_dtype):
-    """CUDA tensor -> host numpy array of np_dtype (conversion done on the device: PCIe beats one CPU core)."""
+    """CUDA tensor -> host numpy array of np_dtype.
+
+    The dtype conversion runs on the device and the copy lands in page-locked memory (torch's caching host
+    allocator), so the transfer is one DMA at PCIe speed instead of a staged copy plus a single-core cast.
+    The returned array owns that buffer (it is recycled when the array is garbage collected)."""
+    import torch
     np_dtype = np.dtype(np_dtype)
     if np_dtype == np.float64:
         t = t.double()
     elif np_dtype == np.float32:
         t = t.float()
-    out = t.cpu().numpy()
+    t = t.contiguous()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    out = host.numpy()
     if out.dtype != np_dtype:
         out = out.astype(np_dtype)
     return out
