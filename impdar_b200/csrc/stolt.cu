@@ -183,10 +183,19 @@ struct StoltPlans {
 static std::map<std::tuple<int, int, int>, StoltPlans> g_plans;  // (device, S, T)
 static std::mutex g_plans_mu;
 
-static int g_stolt_force_r2c = 0;
+// 0 auto (five-pass kernels of stolt_fft.cu for the power-of-two shapes they cover, else the cuFFT paired-trace
+// pipeline for even shapes, else cuFFT R2C/C2R); 1 force cuFFT R2C/C2R; 2 force cuFFT paired; 3 force five-pass.
+static int g_stolt_mode = 0;
+static int g_stolt_stop_after = 0;
+static int g_stolt_last = 0;
 static inline bool stolt_use_paired(int S, int T) {
-    return !g_stolt_force_r2c && (S % 2 == 0) && (T % 2 == 0) && S >= 4 && T >= 4;
+    return g_stolt_mode != 1 && (S % 2 == 0) && (T % 2 == 0) && S >= 4 && T >= 4;
 }
+
+bool stolt_fft_supported(int S, int T);
+size_t stolt_fft_workspace_bytes(int S, int T);
+int stolt_fft_run(const float *data, float *out, int S, int T, double dt, double dx, double vel, double htaper,
+                  double vtaper, int trunc_int, void *workspace, int stop_after, cudaStream_t st);
 
 static int get_plans(int S, int T, StoltPlans &out) {
     int dev = 0;
@@ -259,9 +268,21 @@ int impdar_stolt_f32(const float *data, float *out, int S, int T, int batch, dou
     float2 *bufKK = (float2 *)w;
     float2 *bufFK = (float2 *)(w + (((cplx > real ? cplx : real) + 255) & ~(size_t)255));
 
+    IMPDAR_CHECK_ARG(!(g_stolt_mode == 3 && !stolt_fft_supported(S, T)),
+                     "stolt: the five-pass pipeline does not cover snum = %d, tnum = %d", S, T);
+    if ((g_stolt_mode == 0 || g_stolt_mode == 3) && stolt_fft_supported(S, T)) {
+        for (int b = 0; b < batch; ++b) {
+            int rcf = stolt_fft_run(data + (size_t)b * S * T, out + (size_t)b * S * T, S, T, dt, dx, vel, htaper, vtaper,
+                                    trunc_int, workspace, g_stolt_stop_after, st);
+            if (rcf) return rcf;
+        }
+        g_stolt_last = 3;
+        return IMPDAR_B200_OK;
+    }
     StoltPlans pl;
     int rc = get_plans(S, T, pl);
     if (rc) return rc;
+    g_stolt_last = pl.paired ? 2 : 1;
     if (pl.paired) {
         IMPDAR_CUFFT(cufftSetStream(pl.c2c2d, st));
         StoltPairedParams pp;
@@ -318,7 +339,21 @@ int impdar_stolt_f32(const float *data, float *out, int S, int T, int batch, dou
 
 /* Testing hook: 1 forces the generic R2C/C2R pipeline even when the paired-trace one applies. */
 int impdar_stolt_force_r2c(int on) {
-    g_stolt_force_r2c = on ? 1 : 0;
+    g_stolt_mode = on ? 1 : 0;
+    return IMPDAR_B200_OK;
+}
+
+int impdar_stolt_set_pipeline(int mode) {
+    IMPDAR_CHECK_ARG(mode >= 0 && mode <= 3, "stolt_set_pipeline: 0 auto, 1 cuFFT R2C/C2R, 2 cuFFT paired C2C, 3 five-pass kernels");
+    g_stolt_mode = mode;
+    return IMPDAR_B200_OK;
+}
+
+int impdar_stolt_last_pipeline(void) { return g_stolt_last; }
+
+int impdar_stolt_debug_stop_after(int stage) {
+    IMPDAR_CHECK_ARG(stage >= 0 && stage <= 5, "stolt_debug_stop_after: stage must be in [0, 5]");
+    g_stolt_stop_after = stage;
     return IMPDAR_B200_OK;
 }
 

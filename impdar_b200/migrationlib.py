@@ -163,6 +163,19 @@ def stolt_force_generic(on=True):
     _lib.check(_lib.load().impdar_stolt_force_r2c(int(bool(on))))
 
 
+STOLT_AUTO, STOLT_CUFFT_R2C, STOLT_CUFFT_PAIRED, STOLT_FIVE_PASS = 0, 1, 2, 3
+
+
+def set_stolt_pipeline(mode=STOLT_AUTO):
+    """Pipeline selection (testing / benchmarking): AUTO runs the five-pass hand-written transform kernels for the
+    power-of-two shapes they cover and the cuFFT pipelines otherwise."""
+    _lib.check(_lib.load().impdar_stolt_set_pipeline(int(mode)))
+
+
+def stolt_last_pipeline():
+    return {1: 'cufft_r2c', 2: 'cufft_paired', 3: 'five_pass'}.get(_lib.load().impdar_stolt_last_pipeline(), 'none')
+
+
 def migrationStolt(dat, vel=1.68e8, htaper=100, vtaper=1000):
     """Stolt f-k migration; mirrors mig_python.py:126-208 (output has 2*(snum//2) rows, :202)."""
     print('Stolt Migration (f-k migration) of %.0fx%.0f matrix' % (dat.snum, dat.tnum))

@@ -129,6 +129,16 @@ int impdar_stolt_f32(const float *data, float *out, int snum, int tnum, int batc
 /* Testing hook: 1 forces the generic R2C/C2R pipeline even where the paired-trace C2C pipeline (even snum and
  * tnum) applies; 0 restores automatic selection.                                                      */
 int impdar_stolt_force_r2c(int on);
+/* Pipeline selection: 0 automatic (the five-pass hand-written transform kernels for snum in {512..8192} and tnum in
+ * {8192..131072}, powers of two; otherwise cuFFT paired-trace C2C for even shapes; otherwise cuFFT R2C/C2R),
+ * 1 cuFFT R2C/C2R, 2 cuFFT paired C2C, 3 five-pass kernels (EINVAL at call time for shapes they do not cover). */
+int impdar_stolt_set_pipeline(int mode);
+/* 1, 2 or 3 as above: what the last impdar_stolt_f32 call ran. */
+int impdar_stolt_last_pipeline(void);
+/* Testing hook for the five-pass pipeline: stop after pass 1..5 (0 = run everything).  After pass 1 or 4 `out`
+ * holds W1 (snum x tnum/2 complex); after pass 2 or 3 the workspace (256-byte aligned) holds the transposed half
+ * spectrum (tnum/2 x snum complex).  tests/stolt_stage_model.py restates each stage.                    */
+int impdar_stolt_debug_stop_after(int stage);
 
 /* -------------------------------------- phase shift (mig_python.py:211-287, 361-493) --- */
 /* data (snum, tnum) -> out (snum, tnum).  vmig == NULL: constant velocity `vel` (:396-420);
