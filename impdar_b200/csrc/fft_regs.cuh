@@ -12,15 +12,23 @@ typedef float2 cf;
 #define FFTR_DI __device__ __forceinline__
 
 FFTR_DI cf mk(float x, float y) { return make_float2(x, y); }
-FFTR_DI cf cadd(cf a, cf b) { return mk(a.x + b.x, a.y + b.y); }
-FFTR_DI cf csub(cf a, cf b) { return mk(a.x - b.x, a.y - b.y); }
-FFTR_DI cf cmul(cf a, cf b) { return mk(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x)); }
+// Complex arithmetic on the packed fp32x2 pipe of sm_100 (FADD2 / FMUL2 / FFMA2): an add is one instruction,
+// a multiply two; negations, the lane swap of a multiplication by +-i and scalar broadcasts fold into operand
+// modifiers (checked in SASS: R.F32x2.LO_HI.NP, R.F32).
+FFTR_DI cf cadd(cf a, cf b) { return __fadd2_rn(a, b); }
+FFTR_DI cf csub(cf a, cf b) { return __fadd2_rn(a, mk(-b.x, -b.y)); }
+FFTR_DI cf cmul(cf a, cf b) { return __ffma2_rn(a, mk(b.x, b.x), __fmul2_rn(mk(-a.y, a.x), mk(b.y, b.y))); }
+FFTR_DI cf cmul_conj(cf a, cf b) { return __ffma2_rn(a, mk(b.x, b.x), __fmul2_rn(mk(a.y, -a.x), mk(b.y, b.y))); }  // a * conj(b)
 FFTR_DI cf cconj(cf a) { return mk(a.x, -a.y); }
-FFTR_DI cf cscale(cf a, float s) { return mk(a.x * s, a.y * s); }
+FFTR_DI cf cscale(cf a, float s) { return __fmul2_rn(a, mk(s, s)); }
+FFTR_DI cf cmuli(cf a) { return mk(-a.y, a.x); }    // a * i
+FFTR_DI cf cmulni(cf a) { return mk(a.y, -a.x); }   // a * (-i)
+// s0 * a + s1 * b with real scalars
+FFTR_DI cf clerp(cf a, float s0, cf b, float s1) { return __ffma2_rn(a, mk(s0, s0), __fmul2_rn(b, mk(s1, s1))); }
 // a * w for the forward transform (DIR < 0), a * conj(w) for the inverse; tables hold forward twiddles e^{-i theta}
 template <int DIR>
 FFTR_DI cf cmul_dir(cf a, cf w) {
-    return DIR < 0 ? cmul(a, w) : mk(fmaf(a.x, w.x, a.y * w.y), fmaf(a.y, w.x, -a.x * w.y));
+    return DIR < 0 ? cmul(a, w) : cmul_conj(a, w);
 }
 
 // cos / sin of 2 pi m / 32 as compile-time constants
@@ -51,7 +59,7 @@ FFTR_DI cf twmul32(cf a, int m32) {
     if (m32 == 24) return DIR < 0 ? mk(-a.y, a.x) : mk(a.y, -a.x);
     const float c = cos32(m32);
     const float s = DIR < 0 ? -sin32(m32) : sin32(m32);
-    return mk(fmaf(a.x, c, -a.y * s), fmaf(a.x, s, a.y * c));
+    return cmul(a, mk(c, s));
 }
 
 template <int DIR>

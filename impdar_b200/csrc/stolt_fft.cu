@@ -31,7 +31,6 @@ using namespace fftr;
 
 constexpr int N2 = 256;      // contiguous sub-transform length of a row
 constexpr int NC2 = 16;      // n2 values per P1/P5 tile (128-byte runs)
-constexpr int TILE = 8192;   // complex elements per P1/P5 tile (64 KB)
 
 // ------------------------------------------------------------------------------------------- tables
 __global__ void twiddle_table_kernel(cf *__restrict__ tab, int n, int count) {
@@ -105,15 +104,31 @@ struct RowAParams {
     const cf *twTh;     // w_Th^m, m < Th
 };
 
-template <int N1, int RA, int RB, int DIR>
-__global__ void __launch_bounds__(256) stolt_rowA_kernel(const __grid_constant__ RowAParams p) {
-    static_assert(RA * RB == N1, "radix split");
-    constexpr int NS = TILE / (N1 * NC2);  // rows per tile
-    constexpr int COLS = NS * NC2;
+FFTR_DI void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+FFTR_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+FFTR_DI void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int TILE_A = 4096;  // complex elements per P1/P5 tile (32 KB), double buffered
+
+// Tile = N1 (all strided sub-transform inputs) x NS rows x 16 consecutive n2, laid out [n1][row][n2] so that every
+// global run is 128 contiguous bytes and the transform runs along the slow axis with lanes over (row, n2).
+// N1 = 16 * RB: step 1 is radix 16, step 2 radix RB; slot p = ka * RB + kb holds index k = ka + 16 kb.
+// Loads are cp.async into a double buffer (the next tile streams in while this one is transformed); every
+// address is a per-thread base plus a compile-time offset.
+template <int N1, int DIR>
+__global__ void __launch_bounds__(256, 2) stolt_rowA_kernel(const __grid_constant__ RowAParams p) {
+    constexpr int RB = N1 / 16;
+    constexpr int NS = TILE_A / (N1 * NC2);  // rows per tile = 16 / RB
+    constexpr int COLS = NS * NC2;           // 256 / RB
+    static_assert(RB >= 1 && RB <= 16 && NS * RB == 16, "N1 must be 16, 32, 64, 128 or 256");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cf *tile = reinterpret_cast<cf *>(smem_raw);
-    cf *tab = tile + TILE;         // [N1][NC2]: w_Th^{k1 n2}
-    cf *tw = tab + N1 * NC2;       // [N1]: w_N1^m
+    cf *tiles = reinterpret_cast<cf *>(smem_raw);  // 2 x TILE_A
+    cf *tab = tiles + 2 * TILE_A;                  // [N1][NC2]: w_Th^{k1 n2}
+    cf *tw = tab + N1 * NC2;                       // [N1]: w_N1^m
     const int tid = threadIdx.x;
     const int n2b = blockIdx.x * NC2;
     for (int i = tid; i < N1 * NC2; i += 256) {
@@ -121,57 +136,109 @@ __global__ void __launch_bounds__(256) stolt_rowA_kernel(const __grid_constant__
         tab[i] = p.twTh[(int)(((long long)k1 * n2) % p.Th)];
     }
     for (int i = tid; i < N1; i += 256) tw[i] = p.twTh[i * N2];
-    __syncthreads();
+
     const int row_begin = blockIdx.y * p.rows_per_cta;
-    const int row_end = min(p.S, row_begin + p.rows_per_cta);
-    for (int s0 = row_begin; s0 < row_end; s0 += NS) {
-        // ---- load
-#pragma unroll 4
-        for (int i = 0; i < TILE / 256; ++i) {
-            const int e = i * 256 + tid;
-            const int n2l = e % NC2, sl = (e / NC2) % NS, n1 = e / COLS;
-            const int s = s0 + sl;
-            const int j = n1 * N2 + n2b + n2l;
-            cf val = mk(0.f, 0.f);
-            if (s < p.S) {
-                if (DIR < 0) {
-                    const float2 d = *reinterpret_cast<const float2 *>(p.data + (size_t)s * p.T + 2 * j);
+    const int ntiles = (min(p.S, row_begin + p.rows_per_cta) - row_begin) / NS;
+
+    // ---- per-thread constants of the load: 16-byte chunk c = i * 256 + tid -> (n1, row, piece)
+    const int l_piece = tid & 7, l_sl = (tid >> 3) % NS, l_n1 = (tid >> 3) / NS;
+    const float *gsrc = (DIR < 0 ? p.data : reinterpret_cast<const float *>(p.W1)) + (size_t)(row_begin + l_sl) * p.T +
+                        2 * (l_n1 * N2 + n2b) + l_piece * 4;
+    constexpr int L_STEP = (32 / NS) * N2 * 2;  // floats between the chunks of consecutive i
+    // ---- per-thread constants of the store: element e = i * 256 + tid -> (slot, row, n2l); slot = i * RB + s_pt
+    const int s_n2l = tid & 15, s_sl = (tid >> 4) % NS, s_pt = (tid >> 4) / NS;
+    cf *gdst = p.W1 + (size_t)(row_begin + s_sl) * p.Th + (size_t)(16 * s_pt) * N2 + n2b + s_n2l;
+    const cf *tabs = tab + (16 * s_pt) * NC2 + s_n2l;
+    // ---- taper zones of this CTA's columns (P1): weights differ from 1 only there
+    const bool hzone = (2 * n2b < max(p.hceil, 1)) || (p.T - 2 * ((N1 - 1) * N2 + n2b + NC2) < max(p.hceil, 1)) ||
+                       p.trunc_int;
+
+    auto issue = [&](int t) {
+        cf *dst = tiles + (t & 1) * TILE_A;
+        const float *src = gsrc + (size_t)t * NS * p.T;
+#pragma unroll
+        for (int i = 0; i < TILE_A / 2 / 256; ++i) cp_async16(reinterpret_cast<float4 *>(dst) + i * 256 + tid, src + i * L_STEP);
+        cp_async_commit();
+    };
+    if (ntiles > 0) issue(0);
+    __syncthreads();  // tables
+    for (int t = 0; t < ntiles; ++t) {
+        if (t + 1 < ntiles) {
+            issue(t + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        cf *tile = tiles + (t & 1) * TILE_A;
+        const int s0 = row_begin + t * NS;
+        if (DIR < 0) {
+            const bool vzone = (s0 < max(p.vceil, 1)) || (p.S - s0 - NS < max(p.vceil, 1));
+            if (hzone || vzone) {  // block-uniform: apply the taper to this tile in shared memory
+                for (int e = tid; e < TILE_A; e += 256) {
+                    const int n2l = e % NC2, sl = (e / NC2) % NS, n1 = e / COLS;
+                    const int s = s0 + sl, x = 2 * (n1 * N2 + n2b + n2l);
                     const double v = taper_w(s, p.S, p.vtaper, p.vceil);
-                    const double h0 = taper_w(2 * j, p.T, p.htaper, p.hceil);
-                    const double h1 = taper_w(2 * j + 1, p.T, p.htaper, p.hceil);
-                    if (v == 1.0 && h0 == 1.0 && h1 == 1.0 && !p.trunc_int) {
-                        val = d;
-                    } else {
-                        double a = (double)d.x * h0 * v, b = (double)d.y * h1 * v;  // (data * H) * V, mig_python.py:157
-                        if (p.trunc_int) {
-                            a = trunc(a);
-                            b = trunc(b);
-                        }
-                        val = mk((float)a, (float)b);
+                    const double h0 = taper_w(x, p.T, p.htaper, p.hceil), h1 = taper_w(x + 1, p.T, p.htaper, p.hceil);
+                    const cf d = tile[e];
+                    double a = (double)d.x * h0 * v, b = (double)d.y * h1 * v;  // (data * H) * V, mig_python.py:157
+                    if (p.trunc_int) {
+                        a = trunc(a);
+                        b = trunc(b);
                     }
-                } else {
-                    val = cmul_dir<1>(p.W1[(size_t)s * p.Th + j], tab[n1 * NC2 + n2l]);
+                    tile[e] = mk((float)a, (float)b);
                 }
-            }
-            tile[e] = val;
-        }
-        __syncthreads();
-        tile_fft<RA, RB, DIR, COLS, 0, 256>(tile, tw, 1, COLS, tid);
-        // ---- store
-#pragma unroll 4
-        for (int i = 0; i < TILE / 256; ++i) {
-            const int e = i * 256 + tid;
-            const int n2l = e % NC2, sl = (e / NC2) % NS, pslot = e / COLS;
-            const int s = s0 + sl;
-            const int k = slot_to_k<RA, RB>(pslot);
-            if (s < p.S) {
-                const cf val = tile[e];
-                const size_t o = (size_t)s * p.Th + k * N2 + n2b + n2l;
-                if (DIR < 0) p.W1[o] = cmul(val, tab[k * NC2 + n2l]);
-                else p.W1[o] = val;  // (re, im) = (out[s][2j], out[s][2j+1])
+                __syncthreads();
             }
         }
+        // ---- step 1: radix 16 over q (slots q * RB + r) for every (r, col); P5 first multiplies by conj(w_Th^{k1 n2})
+        {
+            constexpr int ITEMS = RB * COLS / 256;  // = 1
+            static_assert(ITEMS == 1, "one radix-16 item per thread");
+            const int r = tid / COLS, col = tid % COLS;
+            cf v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = tile[(q * RB + r) * COLS + col];
+            if (DIR > 0) {
+                const cf *tq = tab + r * NC2 + (col % NC2);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = cmul_conj(v[q], tq[q * RB * NC2]);
+            }
+            fft_reg<16, DIR>(v);
+            if (RB > 1) {
+#pragma unroll
+                for (int ka = 1; ka < 16; ++ka) v[ka] = cmul_dir<DIR>(v[ka], tw[r * ka]);
+            }
+#pragma unroll
+            for (int ka = 0; ka < 16; ++ka) tile[(ka * RB + r) * COLS + col] = v[ka];
+        }
         __syncthreads();
+        if (RB > 1) {
+            constexpr int ITEMS = 16 * COLS / 256;  // = 16 / RB
+#pragma unroll
+            for (int it = 0; it < ITEMS; ++it) {
+                const int item = tid + it * 256;
+                const int ka = item / COLS, col = item % COLS;
+                cf v[RB];
+#pragma unroll
+                for (int r = 0; r < RB; ++r) v[r] = tile[(ka * RB + r) * COLS + col];
+                fft_reg<RB, DIR>(v);
+#pragma unroll
+                for (int kb = 0; kb < RB; ++kb) tile[(ka * RB + kb) * COLS + col] = v[kb];
+            }
+            __syncthreads();
+        }
+        // ---- store: slot i * RB + s_pt holds index k = i + 16 s_pt
+        {
+            cf *dst = gdst + (size_t)t * NS * p.Th;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                cf val = tile[i * 256 + tid];
+                if (DIR < 0) val = cmul(val, tabs[i * NC2]);
+                dst[i * N2] = val;  // P5: (re, im) = (out[s][2j], out[s][2j+1])
+            }
+        }
+        __syncthreads();  // the tile buffer is refilled by the prefetch of the next iteration
     }
 }
 
@@ -186,13 +253,14 @@ struct RowBParams {
 constexpr int RB_PITCH = 33;
 constexpr int RB_TILE = N2 * RB_PITCH + 16;
 
+// Generic version: handles the self-paired sub-transforms k1 = 0 and k1 = N1/2 (blockIdx.x = 0, 1).
 template <int DIR>
-__global__ void __launch_bounds__(256) stolt_rowB_kernel(const __grid_constant__ RowBParams p) {
+__global__ void __launch_bounds__(256) stolt_rowB_self_kernel(const __grid_constant__ RowBParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf *tile = reinterpret_cast<cf *>(smem_raw);
     cf *tw = tile + RB_TILE;  // [512]
     const int tid = threadIdx.x;
-    const int k1a = blockIdx.x, k1b = (p.N1 - k1a) % p.N1;
+    const int k1a = blockIdx.x * (p.N1 / 2), k1b = (p.N1 - k1a) % p.N1;
     const int nk = (k1a == k1b) ? 1 : 2;
     const int ncols = nk * 16;
     const int s0 = blockIdx.y * 16;
@@ -274,168 +342,340 @@ __global__ void __launch_bounds__(256) stolt_rowB_kernel(const __grid_constant__
     }
 }
 
+FFTR_DI void cp_async8(void *smem_dst, const void *gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+
+// Fast version for the sub-transform pairs (k1, N1 - k1), k1 = 1 .. N1/2 - 1 (blockIdx.x + 1): 32 columns
+// (2 sub-transforms x 16 rows), every shared-memory address is a per-thread base plus a compile-time offset.
+template <int DIR>
+__global__ void __launch_bounds__(256, 3) stolt_rowB_kernel(const __grid_constant__ RowBParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf *tile = reinterpret_cast<cf *>(smem_raw);
+    cf *tw = tile + RB_TILE;  // [512]: w_512^m
+    const int tid = threadIdx.x;
+    const int k1a = blockIdx.x + 1, k1b = p.N1 - k1a;
+    const int s0 = blockIdx.y * 16;
+    const size_t S = (size_t)p.S;
+    const int h = tid >> 4, sl = tid & 15;
+    constexpr int QS = 16 * RB_PITCH + 1;  // address step between slots q*16 + r and (q+1)*16 + r
+
+    if (DIR < 0) {
+        // W1[(s0 + row)][k1*256 + n2] -> tile[slot n2][kidx*16 + row]; thread = n2
+        const cf *srcA = p.W1 + (size_t)s0 * p.Th + k1a * N2 + tid;
+        const cf *srcB = p.W1 + (size_t)s0 * p.Th + k1b * N2 + tid;
+        cf *dst = tile + slot_addr<RB_PITCH, 1>(tid);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            cp_async8(dst + i, srcA + (size_t)i * p.Th);
+            cp_async8(dst + 16 + i, srcB + (size_t)i * p.Th);
+        }
+    } else {
+        // Dt[k1*256 + k2][s0 + row] -> tile[slot k2][kidx*16 + row]; thread = (k2 mod 16 = h, row = sl)
+        const cf *srcA = p.Dt + ((size_t)k1a * N2 + h) * S + s0 + sl;
+        const cf *srcB = p.Dt + ((size_t)k1b * N2 + h) * S + s0 + sl;
+        cf *dst = tile + h * RB_PITCH + sl;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            cp_async8(dst + i * QS, srcA + (size_t)i * 16 * S);
+            cp_async8(dst + i * QS + 16, srcB + (size_t)i * 16 * S);
+        }
+    }
+    cp_async_commit();
+    for (int i = tid; i < 512; i += 256) tw[i] = p.tw512[i];
+    double sn, cs;
+    sincospi(2.0 * (double)k1a / (double)p.T, &sn, &cs);
+    const cf wA = mk((float)cs, (float)(-sn));  // w_T^{k1a}
+    cp_async_wait<0>();
+    __syncthreads();
+
+    auto fft256 = [&]() {
+        // step 1: radix 16 over q (slots q*16 + r), twiddle w_256^{r ka}; items (r, col): col = tid & 31, r = tid>>5 + 8 it
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int r = (tid >> 5) + 8 * it, col = tid & 31;
+            cf *b = tile + r * RB_PITCH + col;
+            cf v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = b[q * QS];
+            fft_reg<16, DIR>(v);
+#pragma unroll
+            for (int ka = 1; ka < 16; ++ka) v[ka] = cmul_dir<DIR>(v[ka], tw[2 * r * ka]);
+#pragma unroll
+            for (int ka = 0; ka < 16; ++ka) b[ka * QS] = v[ka];
+        }
+        __syncthreads();
+        // step 2: radix 16 over r (slots ka*16 + r); items (ka, col)
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int ka = (tid >> 5) + 8 * it, col = tid & 31;
+            cf *b = tile + ka * QS + col;
+            cf v[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = b[r * RB_PITCH];
+            fft_reg<16, DIR>(v);
+#pragma unroll
+            for (int kb = 0; kb < 16; ++kb) b[kb * RB_PITCH] = v[kb];
+        }
+        __syncthreads();
+    };
+
+    if (DIR < 0) {
+        fft256();
+        // untangle pairs: A = (k1a, k2), B = (k1b, 255 - k2), k2 = 16 it + h; slot of k2 = h*16 + it
+        const cf *tA = tile + (h * 16) * RB_PITCH + h + sl;
+        const cf *tB = tile + ((15 - h) * 16 + 15) * RB_PITCH + (15 - h) + 16 + sl;
+        cf *gA = p.Dt + ((size_t)k1a * N2 + h) * S + s0 + sl;
+        cf *gB = p.Dt + ((size_t)k1b * N2 + 255 - h) * S + s0 + sl;
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const cf zA = tA[it * RB_PITCH], zB = tB[-it * RB_PITCH];
+            const cf wk = cmul(wA, tw[h + 16 * it]);  // w_T^{kx}, kx = k1a + N1 k2
+            const cf e = cscale(cadd(zA, cconj(zB)), 0.5f);          // (zA + conj zB) / 2
+            const cf o = cscale(cmulni(csub(zA, cconj(zB))), 0.5f);   // (zA - conj zB) / (2i)
+            gA[(size_t)it * 16 * S] = cadd(e, cmul(wk, o));
+            const cf wkb = mk(-wk.x, wk.y);  // w_T^{T/2 - kx} = -conj(w_T^{kx})
+            gB[-(ptrdiff_t)((size_t)it * 16 * S)] = cadd(cconj(e), cmul(wkb, cconj(o)));
+        }
+    } else {
+        // tangle pairs in place (natural slots): A at slot k2 = 16 it + h, B at slot 255 - k2
+        cf *tA = tile + h * RB_PITCH + sl;
+        cf *tB = tile + (255 - h) * RB_PITCH + 15 + 16 + sl;
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const cf zA = tA[it * QS], zB = tB[-it * QS];
+            const cf wk = cmul(wA, tw[h + 16 * it]);
+            // Zq[k] = (G[k] + conj G[k']) + i (G[k] - conj G[k']) conj(w_T^k)
+            const cf eA = cadd(zA, cconj(zB));
+            const cf dA = cmul_conj(csub(zA, cconj(zB)), wk);
+            tA[it * QS] = cadd(eA, cmuli(dA));
+            const cf wkb = mk(-wk.x, wk.y);
+            const cf eB = cadd(zB, cconj(zA));
+            const cf dB = cmul_conj(csub(zB, cconj(zA)), wkb);
+            tB[-it * QS] = cadd(eB, cmuli(dB));
+        }
+        __syncthreads();
+        fft256();
+        // W1[(s0 + row)][k1*256 + n2] <- tile[slot of n2][kidx*16 + row]; thread = n2, slot = (n2 & 15)*16 + (n2 >> 4)
+        const cf *src = tile + slot_addr<RB_PITCH, 1>((tid & 15) * 16 + (tid >> 4));
+        cf *dA = p.W1 + (size_t)s0 * p.Th + k1a * N2 + tid;
+        cf *dB = p.W1 + (size_t)s0 * p.Th + k1b * N2 + tid;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            dA[(size_t)i * p.Th] = src[i];
+            dB[(size_t)i * p.Th] = src[16 + i];
+        }
+    }
+}
+
 // -------------------------------------------------------------------- P3: column transform + remap + inverse
 struct ColParams {
     cf *Dt;  // (Th, S), in place
     int Th, N1, T;
-    const cf *twS;  // w_S^k, k < S / R3
+    const cf *twS;  // w_S^k, k < 256
+    const cf *tw2;  // w_256^{k t}, [k < 16][t < 16]
     double beta_unit;
     float norm;
 };
 
-template <int SH>
-FFTR_DI int padi(int a) { return a + (a >> SH); }
+FFTR_DI int padi(int a) { return a + (a >> 4); }
 
-// One Stockham step of radix R on the shared-memory sequence: item j reads x[j + t S/R], multiplies by
-// w_{Ls R}^{k t} (k = j mod Ls), transforms, and writes y[(j - k) R + k + t Ls].
-template <int S, int R, int DIR, int NT, int SH, bool TO_GLOBAL>
-FFTR_DI void stockham_step(cf *__restrict__ buf, const cf *__restrict__ tw, int Ls, int tw_stride, int tid,
+struct RemapCol {
+    int Bi;       // floor(beta^2), saturated at 2^30
+    float Bf;     // beta^2 - Bi
+    float b2f;    // beta^2
+    float norm;
+};
+
+// Source row i0, weights w0 = (1 - a) sc, w1 = a sc of output row jj (1 <= jj < NZ) of a column with beta^2 = Bi + Bf:
+// f = sqrt(jj^2 + beta^2) (mig_python.py:188), a = f - i0 = (jj^2 + beta^2 - i0^2) / (f + i0) with the numerator in
+// exact integer arithmetic (no fp64), sc = jj / f * norm (:197); beyond Nyquist the spline is clamped: i0 = NZ-1, a = 1.
+template <int NZ>
+FFTR_DI void remap_coord(int jj, float jjf, const RemapCol &rc, int &i0, float &w0, float &w1) {
+    const int qi = jj * jj + rc.Bi;
+    const float qf = fmaf(jjf, jjf, rc.b2f);
+    float rs;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(qf));
+    const float r0 = qf * rs;
+    const float m = (r0 - 0.5f) + 12582912.0f;             // round(r0 - 0.5): floor(r0) or one off
+    int i = __float_as_int(m) - 0x4B400000;
+    float fi = m - 12582912.0f;
+    if (i * i > qi) {
+        --i;
+        fi -= 1.0f;
+    } else if ((i + 1) * (i + 1) <= qi) {
+        ++i;
+        fi += 1.0f;
+    }
+    const float num = (float)(qi - i * i) + rc.Bf;
+    float a = __fdividef(num, r0 + fi);
+    if (qi >= NZ * NZ) {
+        i = NZ - 1;
+        a = 1.0f;
+    }
+    const float sc = jjf * rs * rc.norm;
+    i0 = i;
+    w1 = a * sc;
+    w0 = sc - w1;
+}
+
+// One Stockham step of radix R (Ls = 16 or 256) on the padded shared-memory sequence: item j reads x[j + t S/R],
+// multiplies by w_{Ls R}^{k t} (k = j mod Ls), transforms, and writes y[(j - k) R + k + t Ls] - to shared memory
+// again or, for the last inverse step, to the global column.
+template <int S, int R, int LS, int DIR, int NT, bool TO_GLOBAL>
+FFTR_DI void stockham_step(cf *__restrict__ buf, const cf *__restrict__ twS, const cf *__restrict__ tw2, int tid,
                            cf *__restrict__ gdst) {
     constexpr int ITEMS = S / R / NT;
-    static_assert(ITEMS >= 1, "too many threads");
+    constexpr int STR = S / R;  // multiple of 16
+    static_assert(ITEMS >= 1 && STR % 16 == 0, "shape");
     cf v[ITEMS][R];
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
         const int j = tid + it * NT;
+        const cf *src = buf + padi(j);
 #pragma unroll
-        for (int t = 0; t < R; ++t) v[it][t] = buf[padi<SH>(j + t * (S / R))];
+        for (int t = 0; t < R; ++t) v[it][t] = src[t * (STR + STR / 16)];
     }
     if (!TO_GLOBAL) __syncthreads();
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
         const int j = tid + it * NT;
-        const int k = j & (Ls - 1);
-        apply_powers<R, DIR>(v[it], tw[k * tw_stride]);
+        const int k = j & (LS - 1);
+        if (LS == 16) {
+            const cf *tq = tw2 + k * 16;
+#pragma unroll
+            for (int t = 1; t < R; ++t) v[it][t] = cmul_dir<DIR>(v[it][t], tq[t]);
+        } else {
+            apply_powers<R, DIR>(v[it], twS[k]);
+        }
         fft_reg<R, DIR>(v[it]);
         const int base = (j - k) * R + k;
+        if (TO_GLOBAL) {
 #pragma unroll
-        for (int t = 0; t < R; ++t) {
-            if (TO_GLOBAL) gdst[base + t * Ls] = v[it][t];
-            else buf[padi<SH>(base + t * Ls)] = v[it][t];
+            for (int t = 0; t < R; ++t) gdst[base + t * LS] = v[it][t];
+        } else {
+            cf *dst = buf + padi(base);
+#pragma unroll
+            for (int t = 0; t < R; ++t) dst[t * (LS + LS / 16)] = v[it][t];
         }
     }
     if (!TO_GLOBAL) __syncthreads();
 }
 
-// remap coordinate of output row jj (1 <= jj < S/2) for beta^2 = b2: source row i0, weight a, scale sc
-FFTR_DI void remap_coord(int jj, double b2, int nz, float norm, int &i0, float &a, float &sc) {
-    const double q = fma((double)jj, (double)jj, b2);
-    const float r0 = sqrtf((float)q);
-    const double r = (double)r0;
-    const double f = fma(fma(-r, r, q), (double)(0.5f / r0), r);  // one Newton step: |rel err| ~ 1e-14
-    const double fq = fmin(f, (double)nz);
-    i0 = min((int)fq, nz - 1);
-    a = (float)(fq - (double)i0);
-    sc = ((float)jj / (float)f) * norm;
-}
-
-template <int S, int R1, int R2, int R3, int NT>
-__global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) stolt_col_kernel(const __grid_constant__ ColParams p) {
-    constexpr int SH = (R1 == 32) ? 5 : 4;
-    constexpr int I1 = S / R1 / NT;
-    static_assert(I1 >= 1 && R1 * R2 * R3 == S, "factorisation");
-    constexpr int NZ = S / 2;
+// S = 16 * 16 * R3.  NT = S/32 threads; thread tid owns the first-step items jA, jB (radix 16, elements j + t S/16) with
+// jB the frequency mirror of jA: element (jA, t) <-> (jB, 15 - t), so every remap coordinate serves two outputs.
+template <int S, int R3>
+__global__ void __launch_bounds__(S / 32, (S >= 8192 ? 2 : (S >= 4096 ? 4 : 8))) stolt_col_kernel(const __grid_constant__ ColParams p) {
+    constexpr int NT = S / 32, NI = S / 16, NZ = S / 2;
+    static_assert(16 * 16 * R3 == S && NT >= 32, "factorisation");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf *buf = reinterpret_cast<cf *>(smem_raw);
-    cf *tw = buf + (S + (S >> SH));
+    cf *twS = buf + (S + S / 16);
+    cf *tw2 = twS + 256;
     const int tid = threadIdx.x;
-    for (int i = tid; i < S / R3; i += NT) tw[i] = p.twS[i];
+    for (int i = tid; i < 256; i += NT) {
+        twS[i] = p.twS[i];
+        tw2[i] = p.tw2[i];
+    }
+    const int jA = (tid == 0) ? 0 : tid, jB = (tid == 0) ? NI / 2 : NI - tid;
 
     for (int c = blockIdx.x; c < p.Th; c += gridDim.x) {
         cf *col = p.Dt + (size_t)c * S;
-        // ---- forward step 1 (radix R1, no twiddle) straight from global memory
-        {
-            cf v[I1][R1];
+        cf vA[16], vB[16];
+        // ---- forward step 1 (radix 16, no twiddle) straight from global memory
 #pragma unroll
-            for (int it = 0; it < I1; ++it) {
-                const int j = tid + it * NT;
+        for (int t = 0; t < 16; ++t) vA[t] = __ldcs(col + jA + t * NI);
 #pragma unroll
-                for (int t = 0; t < R1; ++t) v[it][t] = __ldcs(col + j + t * (S / R1));
-            }
+        for (int t = 0; t < 16; ++t) vB[t] = __ldcs(col + jB + t * NI);
+        fft_reg<16, -1>(vA);
+        fft_reg<16, -1>(vB);
+        __syncthreads();  // the previous column's last shared-memory reads are done (also orders the table fill)
 #pragma unroll
-            for (int it = 0; it < I1; ++it) fft_reg<R1, -1>(v[it]);
-            __syncthreads();  // the previous column's last shared-memory reads are done
+        for (int t = 0; t < 16; ++t) buf[17 * jA + t] = vA[t];
 #pragma unroll
-            for (int it = 0; it < I1; ++it) {
-                const int j = tid + it * NT;
-#pragma unroll
-                for (int t = 0; t < R1; ++t) buf[padi<SH>(j * R1 + t)] = v[it][t];
-            }
-            __syncthreads();
-        }
-        stockham_step<S, R2, -1, NT, SH, false>(buf, tw, R1, S / (R1 * R2), tid, nullptr);
-        stockham_step<S, R3, -1, NT, SH, false>(buf, tw, R1 * R2, 1, tid, nullptr);
-        // buf now holds F[w], natural order
+        for (int t = 0; t < 16; ++t) buf[17 * jB + t] = vB[t];
+        __syncthreads();
+        stockham_step<S, 16, 16, -1, NT, false>(buf, twS, tw2, tid, nullptr);
+        stockham_step<S, R3, 256, -1, NT, false>(buf, twS, tw2, tid, nullptr);
+        // buf now holds F[w], natural order (padded)
 
-        // ---- remap fused with inverse step 1 (radix R1, no twiddle): item j needs Q[j + t S/R1]
+        // ---- remap fused with inverse step 1
+        const int kx = (c / N2) + p.N1 * (c % N2);
+        RemapCol rc;
         {
-            const int kx = (c / N2) + p.N1 * (c % N2);
             const double beta = p.beta_unit * (double)(c == 0 ? p.T / 2 : kx);
             const double b2 = beta * beta;
-            cf v[I1][R1];
-#pragma unroll
-            for (int it = 0; it < I1; ++it) {
-                const int j = tid + it * NT;
-#pragma unroll
-                for (int t = 0; t < R1; ++t) {
-                    const int w = j + t * (S / R1);
-                    cf q = mk(0.f, 0.f);
-                    if (w != 0 && w != NZ) {
-                        const bool neg = w > NZ;
-                        const int jj = neg ? S - w : w;
-                        int i0;
-                        float a, sc;
-                        remap_coord(jj, b2, NZ, p.norm, i0, a, sc);
-                        const float w0 = (1.f - a) * sc, w1 = a * sc;
-                        if (c != 0) {
-                            const int ia = neg ? ((S - i0) & (S - 1)) : i0;
-                            const int ib = neg ? (S - i0 - 1) : (i0 + 1);
-                            const cf f0 = buf[padi<SH>(ia)], f1 = buf[padi<SH>(ib)];
-                            q = mk(fmaf(f0.x, w0, f1.x * w1), fmaf(f0.y, w0, f1.y * w1));
-                        } else {
-                            // packed column: Z = F0 + i FN with F0 (kx = 0) and FN (kx = T/2) Hermitian in w
-                            const cf zj = buf[padi<SH>(jj)], zjm = buf[padi<SH>(S - jj)];
-                            const cf f0 = mk(0.5f * (zj.x + zjm.x), 0.5f * (zj.y - zjm.y));  // F0[jj]
-                            const cf z0 = buf[padi<SH>(i0)], z0m = buf[padi<SH>((S - i0) & (S - 1))];
-                            const cf z1 = buf[padi<SH>(i0 + 1)], z1m = buf[padi<SH>(S - i0 - 1)];
-                            const cf n0 = mk(0.5f * (z0.y + z0m.y), -0.5f * (z0.x - z0m.x));  // FN[i0]
-                            const cf n1 = mk(0.5f * (z1.y + z1m.y), -0.5f * (z1.x - z1m.x));  // FN[i0 + 1]
-                            cf q0 = cscale(f0, p.norm);  // kx = 0: beta = 0, w' = w, scale 1
-                            cf qn = mk(fmaf(n0.x, w0, n1.x * w1), fmaf(n0.y, w0, n1.y * w1));
-                            if (neg) {
-                                q0 = cconj(q0);
-                                qn = cconj(qn);
-                            }
-                            q = mk(q0.x - qn.y, q0.y + qn.x);  // Q0 + i QN
-                        }
-                    }
-                    v[it][t] = q;
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < I1; ++it) fft_reg<R1, 1>(v[it]);
-            __syncthreads();
-#pragma unroll
-            for (int it = 0; it < I1; ++it) {
-                const int j = tid + it * NT;
-#pragma unroll
-                for (int t = 0; t < R1; ++t) buf[padi<SH>(j * R1 + t)] = v[it][t];
-            }
-            __syncthreads();
+            const double bfl = floor(fmin(b2, 1073741824.0));
+            rc.Bi = (int)bfl;
+            rc.Bf = (b2 < 1073741824.0) ? (float)(b2 - bfl) : 0.f;
+            rc.b2f = (float)b2;
+            rc.norm = p.norm;
         }
-        stockham_step<S, R2, 1, NT, SH, false>(buf, tw, R1, S / (R1 * R2), tid, nullptr);
-        stockham_step<S, R3, 1, NT, SH, true>(buf, tw, R1 * R2, 1, tid, col);
+        // positive-frequency output row jj and its mirror S - jj from one coordinate evaluation
+        auto eval = [&](int jj, float jjf, cf &qpos, cf &qneg) {
+            int i0;
+            float w0, w1;
+            remap_coord<NZ>(jj, jjf, rc, i0, w0, w1);
+            if (c != 0) {
+                qpos = clerp(buf[padi(i0)], w0, buf[padi(i0 + 1)], w1);
+                qneg = clerp(buf[padi((S - i0) & (S - 1))], w0, buf[padi(S - i0 - 1)], w1);
+            } else {
+                // packed column: Z = F0 + i FN with F0 (kx = 0) and FN (kx = T/2) Hermitian in w
+                const cf zj = buf[padi(jj)], zjm = cconj(buf[padi(S - jj)]);
+                const cf z0 = buf[padi(i0)], z0m = cconj(buf[padi((S - i0) & (S - 1))]);
+                const cf z1 = buf[padi(i0 + 1)], z1m = cconj(buf[padi(S - i0 - 1)]);
+                const cf q0 = cscale(cadd(zj, zjm), 0.5f * rc.norm);  // kx = 0: beta = 0, w' = w, scale 1
+                const cf n0 = cscale(cmulni(csub(z0, z0m)), 0.5f);    // FN[i0]
+                const cf n1 = cscale(cmulni(csub(z1, z1m)), 0.5f);    // FN[i0 + 1]
+                const cf qn = clerp(n0, w0, n1, w1);
+                qpos = cadd(q0, cmuli(qn));                 // Q0 + i QN
+                qneg = cadd(cconj(q0), cmuli(cconj(qn)));   // both Hermitian
+            }
+        };
+        if (tid != 0) {
+            const float fA = (float)jA, fB = (float)jB;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                eval(jA + t * NI, fA + (float)(t * NI), vA[t], vB[15 - t]);
+                eval(jB + t * NI, fB + (float)(t * NI), vB[t], vA[15 - t]);
+            }
+        } else {
+            // item 0: w = t NI, mirror (item 0, 16 - t); w = 0 and w = S/2 are zero.  item NI/2: mirror (same item, 15 - t)
+            vA[0] = mk(0.f, 0.f);
+            vA[8] = mk(0.f, 0.f);
+#pragma unroll
+            for (int t = 1; t < 8; ++t) eval(t * NI, (float)(t * NI), vA[t], vA[16 - t]);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) eval(NI / 2 + t * NI, (float)(NI / 2 + t * NI), vB[t], vB[15 - t]);
+        }
+        fft_reg<16, 1>(vA);
+        fft_reg<16, 1>(vB);
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 16; ++t) buf[17 * jA + t] = vA[t];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) buf[17 * jB + t] = vB[t];
+        __syncthreads();
+        stockham_step<S, 16, 16, 1, NT, false>(buf, twS, tw2, tid, nullptr);
+        stockham_step<S, R3, 256, 1, NT, true>(buf, twS, tw2, tid, col);
     }
 }
 
 // ---------------------------------------------------------------------------------------- host side
 struct Tables {
-    cf *twTh = nullptr, *tw512 = nullptr, *twS = nullptr;
+    cf *twTh = nullptr, *tw512 = nullptr, *twS = nullptr, *tw2 = nullptr;
 };
+
+__global__ void twiddle_prod_table_kernel(cf *__restrict__ tab) {  // w_256^{k t}, [16][16]
+    const int k = threadIdx.x >> 4, t = threadIdx.x & 15;
+    double s, c;
+    sincospi(2.0 * (double)(k * t) / 256.0, &s, &c);
+    tab[threadIdx.x] = mk((float)c, (float)(-s));
+}
 static std::map<std::tuple<int, int, int>, Tables> g_tables;  // (device, S, T)
 static std::mutex g_tables_mu;
 
-static int col_r3(int S) { return S >= 4096 ? 16 : S / 256; }
 
 static int get_tables(int S, int T, cudaStream_t st, Tables &out) {
     int dev = 0;
@@ -448,35 +688,37 @@ static int get_tables(int S, int T, cudaStream_t st, Tables &out) {
         return IMPDAR_B200_OK;
     }
     const int Th = T / 2;
-    const int nS = S / col_r3(S);
+    const int nS = 256;
     cf *mem = nullptr;
-    IMPDAR_CUDA(cudaMalloc((void **)&mem, (size_t)(Th + 512 + nS) * sizeof(cf)));
+    IMPDAR_CUDA(cudaMalloc((void **)&mem, (size_t)(Th + 512 + nS + 256) * sizeof(cf)));
     Tables t;
     t.twTh = mem;
     t.tw512 = mem + Th;
     t.twS = mem + Th + 512;
+    t.tw2 = mem + Th + 512 + nS;
     twiddle_table_kernel<<<(Th + 255) / 256, 256, 0, st>>>(t.twTh, Th, Th);
     IMPDAR_LAUNCH_CHECK();
     twiddle_table_kernel<<<2, 256, 0, st>>>(t.tw512, 512, 512);
     IMPDAR_LAUNCH_CHECK();
     twiddle_table_kernel<<<(nS + 255) / 256, 256, 0, st>>>(t.twS, S, nS);
     IMPDAR_LAUNCH_CHECK();
+    twiddle_prod_table_kernel<<<1, 256, 0, st>>>(t.tw2);
+    IMPDAR_LAUNCH_CHECK();
     g_tables[key] = t;
     out = t;
     return IMPDAR_B200_OK;
 }
 
-template <int N1, int RA, int RB, int DIR>
+template <int N1, int DIR>
 static int launch_rowA(const RowAParams &p, cudaStream_t st) {
-    const size_t smem = (size_t)(TILE + N1 * NC2 + N1) * sizeof(cf);
+    const size_t smem = (size_t)(2 * TILE_A + N1 * NC2 + N1) * sizeof(cf);
     static bool attr_done = false;
     if (!attr_done) {
-        IMPDAR_CUDA(cudaFuncSetAttribute(stolt_rowA_kernel<N1, RA, RB, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
+        IMPDAR_CUDA(cudaFuncSetAttribute(stolt_rowA_kernel<N1, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     dim3 grid(N2 / NC2, (p.S + p.rows_per_cta - 1) / p.rows_per_cta);
-    stolt_rowA_kernel<N1, RA, RB, DIR><<<grid, 256, smem, st>>>(p);
+    stolt_rowA_kernel<N1, DIR><<<grid, 256, smem, st>>>(p);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
 }
@@ -484,11 +726,11 @@ static int launch_rowA(const RowAParams &p, cudaStream_t st) {
 template <int DIR>
 static int dispatch_rowA(const RowAParams &p, cudaStream_t st) {
     switch (p.N1) {
-        case 16: return launch_rowA<16, 16, 1, DIR>(p, st);
-        case 32: return launch_rowA<32, 8, 4, DIR>(p, st);
-        case 64: return launch_rowA<64, 16, 4, DIR>(p, st);
-        case 128: return launch_rowA<128, 16, 8, DIR>(p, st);
-        case 256: return launch_rowA<256, 16, 16, DIR>(p, st);
+        case 16: return launch_rowA<16, DIR>(p, st);
+        case 32: return launch_rowA<32, DIR>(p, st);
+        case 64: return launch_rowA<64, DIR>(p, st);
+        case 128: return launch_rowA<128, DIR>(p, st);
+        case 256: return launch_rowA<256, DIR>(p, st);
     }
     set_error("stolt: unsupported row split N1 = %d", p.N1);
     return IMPDAR_B200_EINVAL;
@@ -500,40 +742,42 @@ static int launch_rowB(const RowBParams &p, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
         IMPDAR_CUDA(cudaFuncSetAttribute(stolt_rowB_kernel<DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IMPDAR_CUDA(cudaFuncSetAttribute(stolt_rowB_self_kernel<DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    dim3 grid(p.N1 / 2 + 1, p.S / 16);
+    dim3 grid(p.N1 / 2 - 1, p.S / 16);
     stolt_rowB_kernel<DIR><<<grid, 256, smem, st>>>(p);
+    IMPDAR_LAUNCH_CHECK();
+    dim3 grid_self(2, p.S / 16);  // k1 = 0 and k1 = N1/2
+    stolt_rowB_self_kernel<DIR><<<grid_self, 256, smem, st>>>(p);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
 }
 
-template <int S, int R1, int R2, int R3, int NT>
+template <int S, int R3>
 static int launch_col(const ColParams &p, cudaStream_t st) {
-    constexpr int SH = (R1 == 32) ? 5 : 4;
-    const size_t smem = (size_t)(S + (S >> SH) + S / R3) * sizeof(cf);
+    constexpr int NT = S / 32;
+    const size_t smem = (size_t)(S + S / 16 + 512) * sizeof(cf);
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
-        IMPDAR_CUDA(cudaFuncSetAttribute(stolt_col_kernel<S, R1, R2, R3, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
+        IMPDAR_CUDA(cudaFuncSetAttribute(stolt_col_kernel<S, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int n = 0;
-        IMPDAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stolt_col_kernel<S, R1, R2, R3, NT>, NT, smem));
+        IMPDAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stolt_col_kernel<S, R3>, NT, smem));
         ctas_per_sm = n > 0 ? n : 1;
     }
     int grid = num_sms() * ctas_per_sm;
     if (grid > p.Th) grid = p.Th;
-    stolt_col_kernel<S, R1, R2, R3, NT><<<grid, NT, smem, st>>>(p);
+    stolt_col_kernel<S, R3><<<grid, NT, smem, st>>>(p);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
 }
 
 static int dispatch_col(int S, const ColParams &p, cudaStream_t st) {
     switch (S) {
-        case 512: return launch_col<512, 16, 16, 2, 32>(p, st);
-        case 1024: return launch_col<1024, 16, 16, 4, 64>(p, st);
-        case 2048: return launch_col<2048, 16, 16, 8, 128>(p, st);
-        case 4096: return launch_col<4096, 16, 16, 16, 256>(p, st);
-        case 8192: return launch_col<8192, 32, 16, 16, 256>(p, st);
+        case 1024: return launch_col<1024, 4>(p, st);
+        case 2048: return launch_col<2048, 8>(p, st);
+        case 4096: return launch_col<4096, 16>(p, st);
+        case 8192: return launch_col<8192, 32>(p, st);
     }
     set_error("stolt: unsupported column length %d", S);
     return IMPDAR_B200_EINVAL;
@@ -542,7 +786,7 @@ static int dispatch_col(int S, const ColParams &p, cudaStream_t st) {
 }  // namespace sfft
 
 bool stolt_fft_supported(int S, int T) {
-    const bool s_ok = (S == 512 || S == 1024 || S == 2048 || S == 4096 || S == 8192);
+    const bool s_ok = (S == 1024 || S == 2048 || S == 4096 || S == 8192);
     const bool t_ok = (T == 8192 || T == 16384 || T == 32768 || T == 65536 || T == 131072);
     return s_ok && t_ok;
 }
@@ -569,7 +813,7 @@ int stolt_fft_run(const float *data, float *out, int S, int T, double dt, double
     RowBParams pb;
     pb.W1 = W1; pb.Dt = W2; pb.S = S; pb.T = T; pb.Th = Th; pb.N1 = N1; pb.tw512 = tb.tw512;
     ColParams pc;
-    pc.Dt = W2; pc.Th = Th; pc.N1 = N1; pc.T = T; pc.twS = tb.twS;
+    pc.Dt = W2; pc.Th = Th; pc.N1 = N1; pc.T = T; pc.twS = tb.twS; pc.tw2 = tb.tw2;
     pc.beta_unit = vel * (double)S * dt / (2.0 * (double)T * dx);
     pc.norm = (float)(1.0 / ((double)S * (double)T));
 

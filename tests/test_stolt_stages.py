@@ -56,7 +56,7 @@ def _run_stage(x, stage, htaper, vtaper):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("S,T", [(512, 8192), (2048, 16384), (1024, 32768)])
+@pytest.mark.parametrize("S,T", [(1024, 8192), (2048, 16384), (1024, 32768)])
 def test_stages_match_model(S, T):
     x = _input(S, T, S + T)
     ht, vt = 10, 20
@@ -84,7 +84,7 @@ def test_stages_match_model(S, T):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("S,T", [(512, 8192), (4096, 8192), (8192, 8192), (2048, 65536), (1024, 131072)])
+@pytest.mark.parametrize("S,T", [(1024, 8192), (4096, 8192), (8192, 8192), (2048, 65536), (1024, 131072)])
 def test_five_pass_vs_oracle(S, T):
     import torch
     from impdar_b200 import migrationlib as ml
