@@ -104,16 +104,33 @@ FFTR_DI void fft_reg(cf *v) {
     }
 }
 
-// v[t] *= w^t (forward twiddle w; the inverse uses conj(w)); powers by halving, depth log2(R)
+// v[t] *= w^t (forward twiddle w; the inverse uses conj(w)).  Four interleaved chains c_r = w^r (w^4)^m keep only
+// five twiddles live (a full power table would double the register footprint of a radix-32 item) and bound the
+// rounding error growth at R/4 + 2 multiplications.
 template <int R, int DIR>
 FFTR_DI void apply_powers(cf *v, cf w) {
     if (DIR > 0) w.y = -w.y;
-    cf p[R > 1 ? R : 2];
-    p[1] = w;
+    if constexpr (R <= 4) {
+        cf p = w;
 #pragma unroll
-    for (int t = 2; t < R; ++t) p[t] = cmul(p[t / 2], p[t - t / 2]);
+        for (int t = 1; t < R; ++t) {
+            v[t] = cmul(v[t], p);
+            if (t + 1 < R) p = cmul(p, w);
+        }
+    } else {
+        const cf w2 = cmul(w, w);
+        const cf w4 = cmul(w2, w2);
+        cf c[4];
+        c[0] = w4;  // first used at t = 4
+        c[1] = w;
+        c[2] = w2;
+        c[3] = cmul(w2, w);
 #pragma unroll
-    for (int t = 1; t < R; ++t) v[t] = cmul(v[t], p[t]);
+        for (int t = 1; t < R; ++t) {
+            v[t] = cmul(v[t], c[t & 3]);
+            if (t + 4 < R) c[t & 3] = cmul(c[t & 3], w4);
+        }
+    }
 }
 
 }  // namespace fftr

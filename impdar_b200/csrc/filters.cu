@@ -214,13 +214,61 @@ struct IirCoef {
     double zi[32];
 };
 
+// One step of the transposed direct-form II recurrence (scipy.signal.lfilter).  The feed-forward halves
+// t_i = b_{i+1} x + z_{i+1} do not depend on y, so the serial chain per sample is two DFMA (y, then z_0).
 template <typename T, int NS>
 __device__ __forceinline__ double iir_step(double xv, double (&z)[NS], const IirCoef &c) {
     const double yv = fma(c.b[0], xv, z[0]);
 #pragma unroll
-    for (int i = 0; i < NS - 1; ++i) z[i] = fma(c.b[i + 1], xv, fma(-c.a[i + 1], yv, z[i + 1]));
-    z[NS - 1] = fma(c.b[NS], xv, -c.a[NS] * yv);
+    for (int i = 0; i < NS - 1; ++i) z[i] = fma(-c.a[i + 1], yv, fma(c.b[i + 1], xv, z[i + 1]));
+    z[NS - 1] = fma(-c.a[NS], yv, c.b[NS] * xv);
     return yv;
+}
+
+// Software-pipelined recurrence over n strided samples: the next block of FF_U inputs is in flight while the current
+// block runs through the (serial, fp64-pipe bound) recurrence, so the HBM latency hides behind 21 DFMA per sample.
+constexpr int FF_U = 16;
+
+// `src` walks n samples with stride `ss` elements (negative = backwards), each mapped through `pre` (the odd
+// extension 2 x_edge - x of the pads, or the identity); results go to `dst` with stride `ds` when STORE.
+template <typename T, typename BUF, int NS, bool STORE, typename Pre>
+__device__ __forceinline__ void iir_run(int n, double (&z)[NS], const IirCoef &c, const T *__restrict__ src,
+                                        long long ss, T *__restrict__ dst, long long ds, Pre pre) {
+    BUF cur[FF_U], nxt[FF_U];
+    int i = 0;
+    if (n >= FF_U) {
+#pragma unroll
+        for (int u = 0; u < FF_U; ++u) cur[u] = pre(src[u * ss]);
+        src += FF_U * ss;
+        for (; i + 2 * FF_U <= n; i += FF_U) {
+#pragma unroll
+            for (int u = 0; u < FF_U; ++u) nxt[u] = pre(src[u * ss]);
+            src += FF_U * ss;
+#pragma unroll
+            for (int u = 0; u < FF_U; ++u) {
+                const double yv = iir_step<T, NS>((double)cur[u], z, c);
+                if (STORE) dst[u * ds] = (T)yv;
+            }
+            if (STORE) dst += FF_U * ds;
+#pragma unroll
+            for (int u = 0; u < FF_U; ++u) cur[u] = nxt[u];
+        }
+#pragma unroll
+        for (int u = 0; u < FF_U; ++u) {
+            const double yv = iir_step<T, NS>((double)cur[u], z, c);
+            if (STORE) dst[u * ds] = (T)yv;
+        }
+        if (STORE) dst += FF_U * ds;
+        i += FF_U;
+    }
+    for (; i < n; ++i) {
+        const double yv = iir_step<T, NS>((double)pre(*src), z, c);
+        src += ss;
+        if (STORE) {
+            *dst = (T)yv;
+            dst += ds;
+        }
+    }
 }
 
 template <typename T, int NS>
@@ -240,52 +288,26 @@ __global__ void __launch_bounds__(64) filtfilt_kernel(const T *__restrict__ x, T
     const double x0 = (double)xb[0];
     const double xl = (double)xb[(long long)(S - 1) * st];
     double z[NS];
-    // ---- forward over the odd-extended trace
+    // ---- forward over the odd-extended trace (scipy.signal.filtfilt, padtype='odd')
     {
         const double e0 = (padlen > 0) ? 2.0 * x0 - (double)xb[(long long)padlen * st] : x0;
 #pragma unroll
         for (int i = 0; i < NS; ++i) z[i] = c.zi[i] * e0;
     }
-    int k = 0;
-    for (; k < padlen; ++k) {
-        const double xv = 2.0 * x0 - (double)xb[(long long)(padlen - k) * st];
-        wk[(long long)k * st] = (T)iir_step<T, NS>(xv, z, c);
-    }
-    {
-        int i = 0;
-        for (; i + 8 <= S; i += 8) {
-            double xv[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) xv[u] = (double)xb[(long long)(i + u) * st];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) wk[(long long)(padlen + i + u) * st] = (T)iir_step<T, NS>(xv[u], z, c);
-        }
-        for (; i < S; ++i)
-            wk[(long long)(padlen + i) * st] = (T)iir_step<T, NS>((double)xb[(long long)i * st], z, c);
-    }
-    for (k = 0; k < padlen; ++k) {
-        const double xv = 2.0 * xl - (double)xb[(long long)(S - 2 - k) * st];
-        wk[(long long)(padlen + S + k) * st] = (T)iir_step<T, NS>(xv, z, c);
-    }
+    iir_run<T, double, NS, true>(padlen, z, c, xb + (long long)padlen * st, -st, wk, st,
+                                 [&](T v) { return 2.0 * x0 - (double)v; });
+    iir_run<T, T, NS, true>(S, z, c, xb, st, wk + (long long)padlen * st, st, [](T v) { return v; });
+    iir_run<T, double, NS, true>(padlen, z, c, xb + (long long)(S - 2) * st, -st, wk + (long long)(padlen + S) * st, st,
+                                 [&](T v) { return 2.0 * xl - (double)v; });
     // ---- backward over the forward output
     {
         const double e0 = (double)wk[(long long)(L - 1) * st];
 #pragma unroll
         for (int i = 0; i < NS; ++i) z[i] = c.zi[i] * e0;
     }
-    for (k = L - 1; k >= padlen + S; --k) (void)iir_step<T, NS>((double)wk[(long long)k * st], z, c);
-    {
-        int i = S - 1;
-        for (; i - 7 >= 0; i -= 8) {
-            double xv[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) xv[u] = (double)wk[(long long)(padlen + i - u) * st];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) yb[(long long)(i - u) * st] = (T)iir_step<T, NS>(xv[u], z, c);
-        }
-        for (; i >= 0; --i)
-            yb[(long long)i * st] = (T)iir_step<T, NS>((double)wk[(long long)(padlen + i) * st], z, c);
-    }
+    iir_run<T, T, NS, false>(padlen, z, c, wk + (long long)(L - 1) * st, -st, (T *)nullptr, 0, [](T v) { return v; });
+    iir_run<T, T, NS, true>(S, z, c, wk + (long long)(padlen + S - 1) * st, -st, yb + (long long)(S - 1) * st, -st,
+                            [](T v) { return v; });
 }
 
 template <typename T, int NS>

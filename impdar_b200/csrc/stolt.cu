@@ -194,7 +194,7 @@ static inline bool stolt_use_paired(int S, int T) {
 
 bool stolt_fft_supported(int S, int T);
 size_t stolt_fft_workspace_bytes(int S, int T);
-int stolt_fft_run(const float *data, float *out, int S, int T, double dt, double dx, double vel, double htaper,
+int stolt_fft_run(const float *data, float *out, int S, int T, int batch, double dt, double dx, double vel, double htaper,
                   double vtaper, int trunc_int, void *workspace, int stop_after, cudaStream_t st);
 
 static int get_plans(int S, int T, StoltPlans &out) {
@@ -242,7 +242,18 @@ using namespace impdar;
 extern "C" {
 
 size_t impdar_stolt_workspace_bytes(int S, int T, int batch) {
-    (void)batch;  // profiles are processed one at a time through the same buffers
+    // cuFFT pipelines: profiles go one at a time through the same buffers.  Five-pass pipeline: one transposed
+    // half spectrum per profile of a launch, up to 4 GiB (larger batches are processed in chunks).
+    if (g_stolt_mode != 1 && g_stolt_mode != 2 && stolt_fft_supported(S, T)) {
+        const size_t per = stolt_fft_workspace_bytes(S, T) - 256;
+        size_t nb = (size_t)(batch < 1 ? 1 : batch);
+        const size_t cap = ((size_t)4 << 30) / per;
+        if (nb > cap) nb = cap < 1 ? 1 : cap;
+        const size_t five = nb * per + 256;
+        const size_t M5 = (size_t)(S / 2 + 1);
+        const size_t generic = 2 * M5 * (size_t)T * sizeof(float2) + 1024;
+        return five > generic ? five : generic;
+    }
     const size_t M = (size_t)(S / 2 + 1);
     const size_t cplx = M * (size_t)T * sizeof(float2);
     const size_t real = (size_t)S * (size_t)T * sizeof(float);
@@ -271,8 +282,13 @@ int impdar_stolt_f32(const float *data, float *out, int S, int T, int batch, dou
     IMPDAR_CHECK_ARG(!(g_stolt_mode == 3 && !stolt_fft_supported(S, T)),
                      "stolt: the five-pass pipeline does not cover snum = %d, tnum = %d", S, T);
     if ((g_stolt_mode == 0 || g_stolt_mode == 3) && stolt_fft_supported(S, T)) {
-        for (int b = 0; b < batch; ++b) {
-            int rcf = stolt_fft_run(data + (size_t)b * S * T, out + (size_t)b * S * T, S, T, dt, dx, vel, htaper, vtaper,
+        // as many profiles per launch as the workspace holds (grid.z <= 65535, batch * T/2 columns fit an int)
+        size_t per = stolt_fft_workspace_bytes(S, T) - 256;
+        int nb_max = (int)((ws_bytes - 256) / per);
+        if (nb_max > 4096) nb_max = 4096;
+        for (int b = 0; b < batch; b += nb_max) {
+            const int nb = (batch - b < nb_max) ? batch - b : nb_max;
+            int rcf = stolt_fft_run(data + (size_t)b * S * T, out + (size_t)b * S * T, S, T, nb, dt, dx, vel, htaper, vtaper,
                                     trunc_int, workspace, g_stolt_stop_after, st);
             if (rcf) return rcf;
         }

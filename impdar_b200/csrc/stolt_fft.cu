@@ -97,7 +97,7 @@ FFTR_DI double taper_w(int i, int n, double len, int iceil) {
 struct RowAParams {
     const float *data;  // P1 input (S, T) real
     cf *W1;             // P1 output / P5 input (S, Th) complex; P5 writes the real image in place
-    int S, T, Th, N1, rows_per_cta;
+    int S, T, Th, N1, rows_per_cta, batch;
     double htaper, vtaper;
     int hceil, vceil;   // ceil(htaper), ceil(vtaper)
     int trunc_int;
@@ -142,12 +142,13 @@ __global__ void __launch_bounds__(256, 2) stolt_rowA_kernel(const __grid_constan
 
     // ---- per-thread constants of the load: 16-byte chunk c = i * 256 + tid -> (n1, row, piece)
     const int l_piece = tid & 7, l_sl = (tid >> 3) % NS, l_n1 = (tid >> 3) / NS;
-    const float *gsrc = (DIR < 0 ? p.data : reinterpret_cast<const float *>(p.W1)) + (size_t)(row_begin + l_sl) * p.T +
+    const size_t boff = (size_t)blockIdx.z * p.S * p.T;  // profile of the batch (floats)
+    const float *gsrc = (DIR < 0 ? p.data : reinterpret_cast<const float *>(p.W1)) + boff + (size_t)(row_begin + l_sl) * p.T +
                         2 * (l_n1 * N2 + n2b) + l_piece * 4;
     constexpr int L_STEP = (32 / NS) * N2 * 2;  // floats between the chunks of consecutive i
     // ---- per-thread constants of the store: element e = i * 256 + tid -> (slot, row, n2l); slot = i * RB + s_pt
     const int s_n2l = tid & 15, s_sl = (tid >> 4) % NS, s_pt = (tid >> 4) / NS;
-    cf *gdst = p.W1 + (size_t)(row_begin + s_sl) * p.Th + (size_t)(16 * s_pt) * N2 + n2b + s_n2l;
+    cf *gdst = p.W1 + boff / 2 + (size_t)(row_begin + s_sl) * p.Th + (size_t)(16 * s_pt) * N2 + n2b + s_n2l;
     const cf *tabs = tab + (16 * s_pt) * NC2 + s_n2l;
     // ---- taper zones of this CTA's columns (P1): weights differ from 1 only there
     const bool hzone = (2 * n2b < max(p.hceil, 1)) || (p.T - 2 * ((N1 - 1) * N2 + n2b + NC2) < max(p.hceil, 1)) ||
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(256, 2) stolt_rowA_kernel(const __grid_constan
 struct RowBParams {
     cf *W1;   // (S, Th)
     cf *Dt;   // (Th, S)
-    int S, T, Th, N1;
+    int S, T, Th, N1, batch;
     const cf *tw512;  // w_512^m
 };
 
@@ -261,6 +262,8 @@ __global__ void __launch_bounds__(256) stolt_rowB_self_kernel(const __grid_const
     cf *tw = tile + RB_TILE;  // [512]
     const int tid = threadIdx.x;
     const int k1a = blockIdx.x * (p.N1 / 2), k1b = (p.N1 - k1a) % p.N1;
+    const size_t boff = (size_t)blockIdx.z * p.S * p.Th;  // profile of the batch (complex elements)
+    cf *const W1 = p.W1 + boff, *const Dt = p.Dt + boff;
     const int nk = (k1a == k1b) ? 1 : 2;
     const int ncols = nk * 16;
     const int s0 = blockIdx.y * 16;
@@ -274,13 +277,13 @@ __global__ void __launch_bounds__(256) stolt_rowB_self_kernel(const __grid_const
         for (int e = tid; e < nk * 4096; e += 256) {
             const int n2 = e & 255, sl = (e >> 8) & 15, kidx = e >> 12;
             const int k1 = kidx ? k1b : k1a;
-            tile[slot_addr<RB_PITCH, 1>(n2) + kidx * 16 + sl] = p.W1[(size_t)(s0 + sl) * p.Th + k1 * N2 + n2];
+            tile[slot_addr<RB_PITCH, 1>(n2) + kidx * 16 + sl] = W1[(size_t)(s0 + sl) * p.Th + k1 * N2 + n2];
         }
     } else {
         for (int e = tid; e < nk * 4096; e += 256) {
             const int sl = e & 15, k2 = (e >> 4) & 255, kidx = e >> 12;
             const int k1 = kidx ? k1b : k1a;
-            tile[slot_addr<RB_PITCH, 1>(k2) + kidx * 16 + sl] = p.Dt[((size_t)k1 * N2 + k2) * S + s0 + sl];
+            tile[slot_addr<RB_PITCH, 1>(k2) + kidx * 16 + sl] = Dt[((size_t)k1 * N2 + k2) * S + s0 + sl];
         }
     }
     __syncthreads();
@@ -302,15 +305,15 @@ __global__ void __launch_bounds__(256) stolt_rowB_self_kernel(const __grid_const
         if (DIR < 0) {
             const size_t oA = ((size_t)k1a * N2 + k2) * S + s0 + sl;
             if (k1a == 0 && k2 == 0) {
-                p.Dt[oA] = mk(zA.x + zA.y, zA.x - zA.y);  // (D[0], D[T/2]), both real
+                Dt[oA] = mk(zA.x + zA.y, zA.x - zA.y);  // (D[0], D[T/2]), both real
             } else {
                 const cf e = mk(0.5f * (zA.x + zB.x), 0.5f * (zA.y - zB.y));    // (zA + conj zB) / 2
                 const cf o = mk(0.5f * (zA.y + zB.y), -0.5f * (zA.x - zB.x));   // (zA - conj zB) / (2i)
-                p.Dt[oA] = cadd(e, cmul(wk, o));
+                Dt[oA] = cadd(e, cmul(wk, o));
                 if (!self) {
                     const cf wkb = mk(-wk.x, wk.y);  // w_T^{T/2 - kx} = -conj(w_T^{kx})
                     const size_t oB = ((size_t)k1b * N2 + k2p) * S + s0 + sl;
-                    p.Dt[oB] = cadd(cconj(e), cmul(wkb, cconj(o)));
+                    Dt[oB] = cadd(cconj(e), cmul(wkb, cconj(o)));
                 }
             }
         } else {
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(256) stolt_rowB_self_kernel(const __grid_const
         for (int e = tid; e < nk * 4096; e += 256) {
             const int n2 = e & 255, sl = (e >> 8) & 15, kidx = e >> 12;
             const int k1 = kidx ? k1b : k1a;
-            p.W1[(size_t)(s0 + sl) * p.Th + k1 * N2 + n2] =
+            W1[(size_t)(s0 + sl) * p.Th + k1 * N2 + n2] =
                 tile[slot_addr<RB_PITCH, 1>(k_to_slot<16, 16>(n2)) + kidx * 16 + sl];
         }
     }
@@ -358,13 +361,15 @@ __global__ void __launch_bounds__(256, 3) stolt_rowB_kernel(const __grid_constan
     const int k1a = blockIdx.x + 1, k1b = p.N1 - k1a;
     const int s0 = blockIdx.y * 16;
     const size_t S = (size_t)p.S;
+    const size_t boff = (size_t)blockIdx.z * p.S * p.Th;  // profile of the batch (complex elements)
+    cf *const W1 = p.W1 + boff, *const Dt = p.Dt + boff;
     const int h = tid >> 4, sl = tid & 15;
     constexpr int QS = 16 * RB_PITCH + 1;  // address step between slots q*16 + r and (q+1)*16 + r
 
     if (DIR < 0) {
         // W1[(s0 + row)][k1*256 + n2] -> tile[slot n2][kidx*16 + row]; thread = n2
-        const cf *srcA = p.W1 + (size_t)s0 * p.Th + k1a * N2 + tid;
-        const cf *srcB = p.W1 + (size_t)s0 * p.Th + k1b * N2 + tid;
+        const cf *srcA = W1 + (size_t)s0 * p.Th + k1a * N2 + tid;
+        const cf *srcB = W1 + (size_t)s0 * p.Th + k1b * N2 + tid;
         cf *dst = tile + slot_addr<RB_PITCH, 1>(tid);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -373,8 +378,8 @@ __global__ void __launch_bounds__(256, 3) stolt_rowB_kernel(const __grid_constan
         }
     } else {
         // Dt[k1*256 + k2][s0 + row] -> tile[slot k2][kidx*16 + row]; thread = (k2 mod 16 = h, row = sl)
-        const cf *srcA = p.Dt + ((size_t)k1a * N2 + h) * S + s0 + sl;
-        const cf *srcB = p.Dt + ((size_t)k1b * N2 + h) * S + s0 + sl;
+        const cf *srcA = Dt + ((size_t)k1a * N2 + h) * S + s0 + sl;
+        const cf *srcB = Dt + ((size_t)k1b * N2 + h) * S + s0 + sl;
         cf *dst = tile + h * RB_PITCH + sl;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -426,8 +431,8 @@ __global__ void __launch_bounds__(256, 3) stolt_rowB_kernel(const __grid_constan
         // untangle pairs: A = (k1a, k2), B = (k1b, 255 - k2), k2 = 16 it + h; slot of k2 = h*16 + it
         const cf *tA = tile + (h * 16) * RB_PITCH + h + sl;
         const cf *tB = tile + ((15 - h) * 16 + 15) * RB_PITCH + (15 - h) + 16 + sl;
-        cf *gA = p.Dt + ((size_t)k1a * N2 + h) * S + s0 + sl;
-        cf *gB = p.Dt + ((size_t)k1b * N2 + 255 - h) * S + s0 + sl;
+        cf *gA = Dt + ((size_t)k1a * N2 + h) * S + s0 + sl;
+        cf *gB = Dt + ((size_t)k1b * N2 + 255 - h) * S + s0 + sl;
 #pragma unroll
         for (int it = 0; it < 16; ++it) {
             const cf zA = tA[it * RB_PITCH], zB = tB[-it * RB_PITCH];
@@ -459,8 +464,8 @@ __global__ void __launch_bounds__(256, 3) stolt_rowB_kernel(const __grid_constan
         fft256();
         // W1[(s0 + row)][k1*256 + n2] <- tile[slot of n2][kidx*16 + row]; thread = n2, slot = (n2 & 15)*16 + (n2 >> 4)
         const cf *src = tile + slot_addr<RB_PITCH, 1>((tid & 15) * 16 + (tid >> 4));
-        cf *dA = p.W1 + (size_t)s0 * p.Th + k1a * N2 + tid;
-        cf *dB = p.W1 + (size_t)s0 * p.Th + k1b * N2 + tid;
+        cf *dA = W1 + (size_t)s0 * p.Th + k1a * N2 + tid;
+        cf *dB = W1 + (size_t)s0 * p.Th + k1b * N2 + tid;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             dA[(size_t)i * p.Th] = src[i];
@@ -472,9 +477,9 @@ __global__ void __launch_bounds__(256, 3) stolt_rowB_kernel(const __grid_constan
 // -------------------------------------------------------------------- P3: column transform + remap + inverse
 struct ColParams {
     cf *Dt;  // (Th, S), in place
-    int Th, N1, T;
+    int Th, N1, T, ncols;  // ncols = batch * Th
     const cf *twS;  // w_S^k, k < 256
-    const cf *tw2;  // w_256^{k t}, [k < 16][t < 16]
+    const cf *tw2;  // w_256^{k t}, [t < 16][k < 16]
     double beta_unit;
     float norm;
 };
@@ -543,9 +548,9 @@ FFTR_DI void stockham_step(cf *__restrict__ buf, const cf *__restrict__ twS, con
         const int j = tid + it * NT;
         const int k = j & (LS - 1);
         if (LS == 16) {
-            const cf *tq = tw2 + k * 16;
+            const cf *tq = tw2 + k;  // [t][k]: lanes run over k, conflict free
 #pragma unroll
-            for (int t = 1; t < R; ++t) v[it][t] = cmul_dir<DIR>(v[it][t], tq[t]);
+            for (int t = 1; t < R; ++t) v[it][t] = cmul_dir<DIR>(v[it][t], tq[t * 16]);
         } else {
             apply_powers<R, DIR>(v[it], twS[k]);
         }
@@ -580,8 +585,9 @@ __global__ void __launch_bounds__(S / 32, (S >= 8192 ? 2 : (S >= 4096 ? 4 : 8)))
     }
     const int jA = (tid == 0) ? 0 : tid, jB = (tid == 0) ? NI / 2 : NI - tid;
 
-    for (int c = blockIdx.x; c < p.Th; c += gridDim.x) {
-        cf *col = p.Dt + (size_t)c * S;
+    for (int cb = blockIdx.x; cb < p.ncols; cb += gridDim.x) {
+        const int c = cb % p.Th;  // column within its profile
+        cf *col = p.Dt + (size_t)cb * S;
         cf vA[16], vB[16];
         // ---- forward step 1 (radix 16, no twiddle) straight from global memory
 #pragma unroll
@@ -667,8 +673,8 @@ struct Tables {
     cf *twTh = nullptr, *tw512 = nullptr, *twS = nullptr, *tw2 = nullptr;
 };
 
-__global__ void twiddle_prod_table_kernel(cf *__restrict__ tab) {  // w_256^{k t}, [16][16]
-    const int k = threadIdx.x >> 4, t = threadIdx.x & 15;
+__global__ void twiddle_prod_table_kernel(cf *__restrict__ tab) {  // w_256^{k t}, [t < 16][k < 16]
+    const int t = threadIdx.x >> 4, k = threadIdx.x & 15;
     double s, c;
     sincospi(2.0 * (double)(k * t) / 256.0, &s, &c);
     tab[threadIdx.x] = mk((float)c, (float)(-s));
@@ -717,7 +723,7 @@ static int launch_rowA(const RowAParams &p, cudaStream_t st) {
         IMPDAR_CUDA(cudaFuncSetAttribute(stolt_rowA_kernel<N1, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    dim3 grid(N2 / NC2, (p.S + p.rows_per_cta - 1) / p.rows_per_cta);
+    dim3 grid(N2 / NC2, (p.S + p.rows_per_cta - 1) / p.rows_per_cta, p.batch);
     stolt_rowA_kernel<N1, DIR><<<grid, 256, smem, st>>>(p);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
@@ -745,10 +751,10 @@ static int launch_rowB(const RowBParams &p, cudaStream_t st) {
         IMPDAR_CUDA(cudaFuncSetAttribute(stolt_rowB_self_kernel<DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    dim3 grid(p.N1 / 2 - 1, p.S / 16);
+    dim3 grid(p.N1 / 2 - 1, p.S / 16, p.batch);
     stolt_rowB_kernel<DIR><<<grid, 256, smem, st>>>(p);
     IMPDAR_LAUNCH_CHECK();
-    dim3 grid_self(2, p.S / 16);  // k1 = 0 and k1 = N1/2
+    dim3 grid_self(2, p.S / 16, p.batch);  // k1 = 0 and k1 = N1/2
     stolt_rowB_self_kernel<DIR><<<grid_self, 256, smem, st>>>(p);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
@@ -766,7 +772,7 @@ static int launch_col(const ColParams &p, cudaStream_t st) {
         ctas_per_sm = n > 0 ? n : 1;
     }
     int grid = num_sms() * ctas_per_sm;
-    if (grid > p.Th) grid = p.Th;
+    if (grid > p.ncols) grid = p.ncols;
     stolt_col_kernel<S, R3><<<grid, NT, smem, st>>>(p);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
@@ -793,8 +799,9 @@ bool stolt_fft_supported(int S, int T) {
 
 size_t stolt_fft_workspace_bytes(int S, int T) { return (size_t)S * (size_t)T * sizeof(float) + 256; }
 
-// Runs passes P1..P5 (stop_after in 1..5 leaves the intermediate buffers in place for the stage tests).
-int stolt_fft_run(const float *data, float *out, int S, int T, double dt, double dx, double vel, double htaper,
+// Runs passes P1..P5 on `batch` stacked profiles at once (the workspace holds batch * S * T floats);
+// stop_after in 1..5 leaves the intermediate buffers in place for the stage tests.
+int stolt_fft_run(const float *data, float *out, int S, int T, int batch, double dt, double dx, double vel, double htaper,
                   double vtaper, int trunc_int, void *workspace, int stop_after, cudaStream_t st) {
     using namespace sfft;
     Tables tb;
@@ -807,13 +814,14 @@ int stolt_fft_run(const float *data, float *out, int S, int T, double dt, double
     RowAParams pa;
     pa.data = data; pa.W1 = W1; pa.S = S; pa.T = T; pa.Th = Th; pa.N1 = N1;
     pa.rows_per_cta = 64;
+    pa.batch = batch;
     pa.htaper = htaper; pa.vtaper = vtaper; pa.trunc_int = trunc_int; pa.twTh = tb.twTh;
     pa.hceil = (htaper == htaper && htaper < 2.0e9) ? (int)ceil(htaper) : 0x7fffffff;
     pa.vceil = (vtaper == vtaper && vtaper < 2.0e9) ? (int)ceil(vtaper) : 0x7fffffff;
     RowBParams pb;
-    pb.W1 = W1; pb.Dt = W2; pb.S = S; pb.T = T; pb.Th = Th; pb.N1 = N1; pb.tw512 = tb.tw512;
+    pb.W1 = W1; pb.Dt = W2; pb.S = S; pb.T = T; pb.Th = Th; pb.N1 = N1; pb.batch = batch; pb.tw512 = tb.tw512;
     ColParams pc;
-    pc.Dt = W2; pc.Th = Th; pc.N1 = N1; pc.T = T; pc.twS = tb.twS; pc.tw2 = tb.tw2;
+    pc.Dt = W2; pc.Th = Th; pc.N1 = N1; pc.T = T; pc.ncols = batch * Th; pc.twS = tb.twS; pc.tw2 = tb.tw2;
     pc.beta_unit = vel * (double)S * dt / (2.0 * (double)T * dx);
     pc.norm = (float)(1.0 / ((double)S * (double)T));
 

@@ -104,3 +104,18 @@ def test_five_pass_vs_oracle(S, T):
     print("stolt %dx%d: five-pass %.2e, cuFFT paired %.2e (rel L2 vs float64 oracle), max abs %.2e"
           % (S, T, e, e2, np.abs(got - want).max()))
     assert e < 1e-5
+
+
+@pytest.mark.gpu
+def test_five_pass_batched_equals_single():
+    """A stack of profiles goes through the five passes in one set of launches (grid.z / column index over the
+    batch); the result must be bit-identical to running the profiles one by one."""
+    import torch
+    from impdar_b200 import migrationlib as ml
+    S, T, B = 1024, 8192, 3
+    x = torch.from_numpy(np.stack([_input(S, T, 100 + b) for b in range(B)])).cuda()
+    got = ml.stolt_device(x, DT, DX, VEL, 10, 20)
+    assert ml.stolt_last_pipeline() == 'five_pass'
+    for b in range(B):
+        one = ml.stolt_device(x[b].contiguous(), DT, DX, VEL, 10, 20)
+        assert torch.equal(got[b], one)
