@@ -23,6 +23,7 @@ PROTOTYPES = {
     "impdar_hfilt_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
     "impdar_hfilt_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
     "impdar_ahfilt_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int]),
+    "impdar_ahfilt_force_rowwise": (_c_int, [_c_int]),
     "impdar_ahfilt_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _c_sz, _vp]),
     "impdar_ahfilt_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _c_sz, _vp]),
     "impdar_filtfilt_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int, _c_int, _c_int]),

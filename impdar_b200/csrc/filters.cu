@@ -207,6 +207,177 @@ __global__ void __launch_bounds__(256) ahfilt_kernel(const T *__restrict__ x, T 
     }
 }
 
+// Strip kernel: a CTA owns a strip of W output traces and a chunk of R sample rows.  Rows are visited in time
+// order; per row the window means of the strip (fp64 prefix sums over the row segment the windows cover: 16
+// consecutive columns per thread, then a block scan of the thread totals) go into a ring of the last seven mean
+// rows, and as soon as a row's 7-tap neighbourhood is complete it is written out - one read of the data (plus
+// w / W halo) and one write.  Requires n = segment length <= 4096 (256 threads x 16).
+constexpr int AH_E = 16;                                  // columns per thread in the scan
+__device__ __forceinline__ int ah_pad(int k) { return k + (k >> 4); }   // 17-double pitch: conflict-free chunks
+
+template <typename T>
+__global__ void __launch_bounds__(256) ahfilt_strip_kernel(const T *__restrict__ x, T *__restrict__ y, int S, int Tn,
+                                                           int w, int tail_lo, const double *__restrict__ taper, int W,
+                                                           int R) {
+    extern __shared__ double smem_d[];
+    double *P = smem_d;                 // [ah_pad(4096)]: inclusive prefix within each thread's chunk
+    double *toff = P + 4096 + 256;      // [256] exclusive offsets of the chunks
+    double *wtot = toff + 256;          // [8]
+    T *ring = reinterpret_cast<T *>(wtot + 8);  // [7][W]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = blockIdx.x * W, c1 = min(Tn, c0 + W);
+    const T *xb = x + (long long)blockIdx.z * S * Tn;
+    T *yb = y + (long long)blockIdx.z * S * Tn;
+    const int h = w / 2;
+    int L0, L1;
+    {
+        int lo, hi;
+        ahfilt_window(c0, Tn, w, tail_lo, lo, hi);
+        L0 = lo;
+        L1 = hi;
+        ahfilt_window(c1 - 1, Tn, w, tail_lo, lo, hi);
+        L0 = min(L0, lo);
+        L1 = max(L1, hi);
+        if (c1 - 1 >= Tn - h) {
+            L0 = min(L0, tail_lo);
+            L1 = Tn;
+        }
+    }
+    const int n = L1 - L0;
+    const int s_begin = blockIdx.y * R, s_end = min(S, s_begin + R);
+    const int r0 = max(0, s_begin - 3), r1 = min(S - 1, s_end + 2);
+    int next_out = s_begin;
+
+    // software pipeline: the row segment of iteration r + 1 and the centre row of this iteration's output are in
+    // flight while row r is scanned
+    constexpr int NV = 4096 / 256;
+    T nxt[NV];
+    {
+        const T *xr = xb + (long long)r0 * Tn + L0;
+#pragma unroll
+        for (int u = 0; u < NV; ++u) nxt[u] = (tid + 256 * u < n) ? xr[tid + 256 * u] : (T)0;
+    }
+    const int nxc = (c1 - c0 + 255) / 256;  // <= 8 centre-row values per thread
+    // per-column window constants (the same for every row): padded prefix indices, chunk ids, 1 / width
+    int wa[8], we[8];
+    double winv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int i = c0 + tid + 256 * u;
+        int lo = 0, hi = 0;
+        if (i < c1) ahfilt_window(i, Tn, w, tail_lo, lo, hi);
+        wa[u] = lo - L0 - 1;
+        we[u] = hi - L0 - 1;
+        winv[u] = 1.0 / (double)(hi - lo);   // inf for an empty window: 0 * inf = NaN like np.mean of an empty slice
+    }
+    for (int r = r0; r <= r1; ++r) {
+        // stage the row segment (coalesced) as doubles
+#pragma unroll
+        for (int u = 0; u < NV; ++u)
+            if (tid + 256 * u < n) P[ah_pad(tid + 256 * u)] = (double)nxt[u];
+        if (r < r1) {
+            const T *xr = xb + (long long)(r + 1) * Tn + L0;
+#pragma unroll
+            for (int u = 0; u < NV; ++u) nxt[u] = (tid + 256 * u < n) ? xr[tid + 256 * u] : (T)0;
+        }
+        T xc[8];
+        {
+            const int s = next_out;  // the row this iteration will (normally) emit
+            const T *xs = xb + (long long)min(s, S - 1) * Tn + c0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xc[u] = (u < nxc && c0 + tid + 256 * u < c1) ? xs[tid + 256 * u] : (T)0;
+        }
+        __syncthreads();
+        // chunk-local inclusive scan: thread t owns columns [16 t, 16 t + 16)
+        double tot = 0.0;
+        {
+            double v[AH_E];
+            double *pc = P + 17 * tid;
+            const int kb = AH_E * tid;
+#pragma unroll
+            for (int e = 0; e < AH_E; ++e) v[e] = (kb + e < n) ? pc[e] : 0.0;
+#pragma unroll
+            for (int e = 0; e < AH_E; ++e) {
+                tot += v[e];
+                v[e] = tot;
+            }
+            if (kb < n) {
+#pragma unroll
+                for (int e = 0; e < AH_E; ++e) pc[e] = v[e];
+            }
+        }
+        // exclusive scan of the 256 chunk totals
+        double inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        {
+            double wo = 0.0;
+            for (int u = 0; u < warp; ++u) wo += wtot[u];
+            toff[tid] = wo + inc - tot;
+        }
+        __syncthreads();
+        T *mrow = ring + (r % 7) * W;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = tid + 256 * u;
+            if (c0 + c < c1) {
+                const int a = wa[u], e = we[u];
+                const double pa = (a < 0) ? 0.0 : P[ah_pad(a)] + toff[a >> 4];
+                const double pe = (e < 0) ? 0.0 : P[ah_pad(e)] + toff[e >> 4];
+                mrow[c] = (T)((pe - pa) * winv[u]);
+            }
+        }
+        __syncthreads();
+        bool first_emit = true;
+        while (next_out < s_end && (next_out + 3 <= r || r == S - 1)) {
+            const int s = next_out++;
+            const bool have_xc = first_emit;  // xc holds row s only for the first row emitted in this iteration
+            first_emit = false;
+            const double tp = taper[s];
+            const T *xs = xb + (long long)s * Tn;
+            T *ys = yb + (long long)s * Tn;
+            if (s >= 3 && s + 3 < S) {
+                // interior: the 7-tap triangular kernel [1 2 3 4 3 2 1] / 16 on rows s-3 .. s+3
+                const T *q0 = ring + ((s - 3) % 7) * W, *q1 = ring + ((s - 2) % 7) * W, *q2 = ring + ((s - 1) % 7) * W;
+                const T *q3 = ring + (s % 7) * W, *q4 = ring + ((s + 1) % 7) * W, *q5 = ring + ((s + 2) % 7) * W;
+                const T *q6 = ring + ((s + 3) % 7) * W;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = tid + 256 * u, i = c0 + c;
+                    if (i < c1) {
+                        // means are stored in T; for float profiles the 7-tap combination also runs in fp32
+                        const T f = (T)0.0625 * (q0[c] + q6[c]) + (T)0.125 * (q1[c] + q5[c]) + (T)0.1875 * (q2[c] + q4[c]) +
+                                    (T)0.25 * q3[c];
+                        const T xv = have_xc ? xc[u] : xs[i];
+                        ys[i] = xv - f * (T)tp;
+                    }
+                }
+            } else {
+                // edges: the kernel on the odd-extended mean trace, folded onto real rows
+                for (int i = c0 + tid; i < c1; i += 256) {
+                    const int c = i - c0;
+                    double f = 0.0;
+#pragma unroll
+                    for (int j = -3; j <= 3; ++j) {
+                        const double cj = (double)(4 - (j < 0 ? -j : j)) / 16.0;
+                        const int q = s + j;
+                        if (q < 0) f += cj * (2.0 * (double)ring[c] - (double)ring[((-q) % 7) * W + c]);
+                        else if (q >= S) f += cj * (2.0 * (double)ring[((S - 1) % 7) * W + c] -
+                                                    (double)ring[((2 * (S - 1) - q) % 7) * W + c]);
+                        else f += cj * (double)ring[(q % 7) * W + c];
+                    }
+                    ys[i] = (T)((double)xs[i] - f * tp);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ filtfilt
 struct IirCoef {
     double b[33];
@@ -407,6 +578,7 @@ static int hfilt_impl(const T *x, T *y, int S, int Tn, int batch, int htr1, int 
 }
 
 static const size_t AHFILT_SMEM_LIMIT = 200 * 1024;
+static int g_ahfilt_force_rowwise = 0;  // testing hook: 1 = always the one-row-per-CTA kernel
 
 template <typename T>
 static int ahfilt_impl(const T *x, T *y, int S, int Tn, int batch, int w, const double *taper, void *ws,
@@ -419,6 +591,42 @@ static int ahfilt_impl(const T *x, T *y, int S, int Tn, int batch, int w, const 
     // python slice start of data[:, tnum - w : tnum]
     int tail_lo = Tn - w;
     if (tail_lo < 0) tail_lo = (tail_lo + Tn < 0) ? 0 : tail_lo + Tn;
+    // strip kernel whenever the prefix buffer of one strip (W + ~w columns) and the 7-row ring fit in shared memory
+    {
+        int W = (sizeof(T) == 4) ? 2048 : 1024;
+        if (W > Tn) W = ((Tn + 31) / 32) * 32;
+        const int h = w / 2;
+        int nmax = 0;
+        for (int c0 = 0; c0 < Tn; c0 += W) {
+            const int c1 = (c0 + W < Tn) ? c0 + W : Tn;
+            int lo0, hi0, lo1, hi1;
+            auto win = [&](int i, int &lo, int &hi) {
+                if (i <= h) { lo = 0; hi = (h + i < Tn) ? h + i : Tn; }
+                else if (i >= Tn - h) { lo = tail_lo; hi = Tn; }
+                else { lo = i - h + 1; hi = i + h; }
+                if (hi < lo) hi = lo;
+            };
+            win(c0, lo0, hi0);
+            win(c1 - 1, lo1, hi1);
+            int L0 = lo0 < lo1 ? lo0 : lo1, L1 = hi0 > hi1 ? hi0 : hi1;
+            if (c1 - 1 >= Tn - h) { if (tail_lo < L0) L0 = tail_lo; L1 = Tn; }
+            if (L1 - L0 > nmax) nmax = L1 - L0;
+        }
+        const size_t smem_strip = (size_t)(4096 + 256 + 256 + 8) * sizeof(double) + (size_t)7 * W * sizeof(T);
+        if (nmax <= 4096 && g_ahfilt_force_rowwise == 0) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                IMPDAR_CUDA(cudaFuncSetAttribute(ahfilt_strip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                attr_done = true;
+            }
+            const int R = 64;
+            dim3 grid((Tn + W - 1) / W, (S + R - 1) / R, batch);
+            IMPDAR_CHECK_ARG(batch <= 65535 && grid.y <= 65535, "ahfilt: batch too large");
+            ahfilt_strip_kernel<T><<<grid, 256, smem_strip, (cudaStream_t)stream>>>(x, y, S, Tn, w, tail_lo, taper, W, R);
+            IMPDAR_LAUNCH_CHECK();
+            return IMPDAR_B200_OK;
+        }
+    }
     const long long rows = (long long)batch * S;
     const size_t need_smem = (size_t)(Tn + 1) * sizeof(double);
     long long grid = rows;
@@ -478,6 +686,10 @@ size_t impdar_ahfilt_workspace_bytes(int S, int T, int batch) {
     const size_t need_smem = (size_t)(T + 1) * sizeof(double);
     if (need_smem <= AHFILT_SMEM_LIMIT) return 0;
     return (size_t)num_sms() * 4 * (size_t)(T + 1) * sizeof(double);
+}
+int impdar_ahfilt_force_rowwise(int on) {
+    g_ahfilt_force_rowwise = on ? 1 : 0;
+    return IMPDAR_B200_OK;
 }
 int impdar_ahfilt_f32(const float *x, float *y, int S, int T, int batch, int w, const double *taper, void *ws,
                       size_t ws_bytes, void *stream) {

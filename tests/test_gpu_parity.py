@@ -135,6 +135,37 @@ def test_ahfilt_golden(name):
     assert rel_l2(d32.data, g["out"]) < TOL
 
 
+@pytest.mark.parametrize("S,T,w", [(300, 5000, 7), (300, 5000, 100), (130, 5000, 1001), (130, 5000, 4000),
+                                   (70, 3000, 6000), (200, 8192, 1000), (64, 2500, 2)])
+def test_ahfilt_strip_vs_oracle(S, T, w):
+    """The strip kernel (rolling 7-row ring, fp64 prefix sums per row segment) against the float64 oracle on shapes with
+    several strips, odd / even / oversized windows and a DC offset; and against the one-row-per-CTA kernel."""
+    import torch
+    from oracle import filtering as of
+    from impdar_b200 import _lib, filtering as fl
+    rng = np.random.default_rng(S + T + w)
+    x = (rng.standard_normal((S, T)) + 25.0).astype(np.float32)
+    tt = np.arange(S) * 0.01
+    want = of.adaptivehfilt(x.astype(np.float64), tt, w)
+    tp = np.exp(-tt * 0.05) / np.exp(-tt[0] * 0.05)
+    xd = torch.from_numpy(x).cuda()
+    got = fl.adaptivehfilt_device(xd, 'f32', tp, w).cpu().numpy()
+    lib = _lib.load()
+    lib.impdar_ahfilt_force_rowwise(1)
+    try:
+        got_row = fl.adaptivehfilt_device(xd, 'f32', tp, w).cpu().numpy()
+    finally:
+        lib.impdar_ahfilt_force_rowwise(0)
+    m = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), m)
+    assert _report("ahfilt strip %dx%d w%d" % (S, T, w), got[m], want[m]) < TOL
+    assert rel_l2(got_row[m], want[m]) < TOL
+    # batch of two profiles == the profiles one by one
+    xb = torch.stack([xd, xd.flip(0).contiguous()])
+    gb = fl.adaptivehfilt_device(xb, 'f32', tp, w)
+    assert torch.equal(gb[0].nan_to_num(), torch.from_numpy(got).cuda().nan_to_num())
+
+
 @pytest.mark.parametrize("name", golden_names(contains="_vbp_"))
 def test_vbp_golden(name):
     g = load_golden(name)
