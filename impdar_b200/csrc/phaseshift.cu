@@ -250,6 +250,256 @@ __global__ void __launch_bounds__(PS_THREADS, 1) phsh_layered_kernel(const __gri
     }
 }
 
+// =====================================================================================================
+// (+w, -w) pair kernels.  The phase of the reference is odd in w (phi(-w) = -phi(w)) while the propagating /
+// evanescent decision depends on w^2 only, so the two bins share one square root, one sincos and one mask:
+//     FK[+w] e^{+i phi} + FK[-w] e^{-i phi} = cos(phi) A + i sin(phi) B,   A = FK[+w] + FK[-w], B = FK[+w] - FK[-w].
+// That halves the MUFU and fp64 work per migrated sample and replaces two complex multiplies by four FMAs
+// (two FFMA2 on the packed fp32x2 pipe).  States are the pairs s = 0 .. nt/2 - 1 (s = 0 is the single bin w = 0,
+// A = B = FK[0]); only pairs that can still propagate get a thread slot; the unpaired Nyquist bin
+// (cosine only, see the header) is added at commit time (constant velocity) or by a one-thread-per-kx kernel.
+constexpr int PP_THREADS = 256;
+constexpr int PP_PER = 8;
+constexpr int PP_STATES = PP_THREADS * PP_PER;
+
+__device__ __forceinline__ float2 pp_mk(float x, float y) { return make_float2(x, y); }
+__device__ __forceinline__ float2 pp_cmul(float2 a, float2 b) {
+    return __ffma2_rn(a, pp_mk(b.x, b.x), __fmul2_rn(pp_mk(-a.y, a.x), pp_mk(b.y, b.y)));
+}
+// acc + cs * A + i sn * B
+__device__ __forceinline__ float2 pp_acc(float2 acc, float cs, float sn, float2 A, float2 B) {
+    return __ffma2_rn(pp_mk(-B.y, B.x), pp_mk(sn, sn), __ffma2_rn(A, pp_mk(cs, cs), acc));
+}
+
+template <int NW>
+__device__ __forceinline__ void pp_park(float2 part, float2 (*buf)[NW], int b) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        part.x += __shfl_xor_sync(0xffffffffu, part.x, o);
+        part.y += __shfl_xor_sync(0xffffffffu, part.y, o);
+    }
+    if ((threadIdx.x & 31) == 0) buf[b][threadIdx.x >> 5] = part;
+}
+
+// Sum the warps' partials of one tau block into TK[tau, k] (scaled); `nyq_const` adds the constant-velocity
+// Nyquist term FK[nt/2, k] cos((tau + 1) phi).
+template <int NW>
+__device__ __forceinline__ void pp_commit(const PhshParams &p, float2 (*buf)[NW], int k, int tb0, bool accumulate,
+                                          bool nyq_const) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < PS_TB; b += blockDim.x) {
+        const int tau = tb0 + b;
+        if (tau < p.S) {
+            float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                s.x += buf[b][w].x;
+                s.y += buf[b][w].y;
+            }
+            if (nyq_const && p.nt >= 2) {
+                const double w = ps_omega(p.nt / 2, p.nt, p.dt);
+                const double vk = p.vel * ps_kx(k, p.T, p.dx) / 2.0;
+                if (vk * vk < w * w) {
+                    const double phi = w * p.dt * sqrt(1.0 - vk * vk / (w * w));
+                    const float cn = (float)cos((double)(tau + 1) * phi);
+                    const float2 f = p.FK[(size_t)(p.nt / 2) * p.K + k];
+                    s.x = fmaf(f.x, cn, s.x);
+                    s.y = fmaf(f.y, cn, s.y);
+                }
+            }
+            s.x *= p.inv_s;
+            s.y *= p.inv_s;
+            float2 *dst = p.TK + (size_t)tau * p.K + k;
+            if (accumulate) {
+                const float2 o = *dst;
+                s.x += o.x;
+                s.y += o.y;
+            }
+            *dst = s;
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void pp_load_pair(const PhshParams &p, int s, int k, float2 &A, float2 &B) {
+    const float2 fp = p.FK[(size_t)s * p.K + k];
+    if (s == 0) {
+        A = fp;
+        B = fp;
+    } else {
+        const float2 fm = p.FK[(size_t)(p.nt - s) * p.K + k];
+        A = make_float2(fp.x + fm.x, fp.y + fm.y);
+        B = make_float2(fp.x - fm.x, fp.y - fm.y);
+    }
+}
+
+// ---- constant velocity (:396-420): rotation recurrence r *= e^{i phi}, re-seeded every PS_TB steps from fp64 seeds
+__global__ void __launch_bounds__(PP_THREADS, 2) phsh_const_pair_kernel(const __grid_constant__ PhshParams p) {
+    __shared__ float2 Rb[PP_PER][PP_THREADS];    // e^{i phi tb0}
+    __shared__ float2 Z64[PP_PER][PP_THREADS];   // e^{i phi PS_TB}
+    __shared__ float2 buf[PS_TB][PP_THREADS / 32];
+    const int tid = threadIdx.x;
+    const int k = blockIdx.x;
+    const int nh = max(1, p.nt / 2);  // nt == 1: the single bin w = 0
+    const double vk = p.vel * ps_kx(k, p.T, p.dx) / 2.0;
+    const double vkx2 = vk * vk;  // (vmig*kx/2)^2   (:411)
+    // pairs below s ~ vk nt dt / 2 pi are evanescent for every tau (:412); start one below the estimate
+    int s_first = (int)fmin((double)nh, floor(vk * (double)p.nt * p.dt * 0.15915494309189535)) - 1;
+    if (s_first < 0) s_first = 0;
+
+    int pass = 0;
+    for (int base = s_first; base < nh || pass == 0; base += PP_STATES, ++pass) {
+        float2 z[PP_PER], A[PP_PER], B[PP_PER];
+#pragma unroll
+        for (int i = 0; i < PP_PER; ++i) {
+            const int s = base + tid + i * PP_THREADS;
+            z[i] = make_float2(1.f, 0.f);
+            A[i] = make_float2(0.f, 0.f);
+            B[i] = A[i];
+            float2 z64 = z[i];
+            if (s < nh) {
+                const double w = ps_omega(s, p.nt, p.dt);
+                if (vkx2 < w * w) {  // propagating (:412)
+                    const double phi = w * p.dt * sqrt(1.0 - vkx2 / (w * w));  // = -phase (:415); cp = e^{+i phi}
+                    double sn, cs;
+                    sincos(phi, &sn, &cs);
+                    z[i] = make_float2((float)cs, (float)sn);
+                    sincos(phi * (double)PS_TB, &sn, &cs);
+                    z64 = make_float2((float)cs, (float)sn);
+                    pp_load_pair(p, s, k, A[i], B[i]);
+                }
+            }
+            Rb[i][tid] = make_float2(1.f, 0.f);
+            Z64[i][tid] = z64;
+        }
+        for (int tb0 = 0; tb0 < p.S; tb0 += PS_TB) {
+            float2 r[PP_PER];
+#pragma unroll
+            for (int i = 0; i < PP_PER; ++i) r[i] = Rb[i][tid];
+            const int nb = min(PS_TB, p.S - tb0);
+            for (int b = 0; b < nb; ++b) {
+                float2 part = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < PP_PER; ++i) {
+                    r[i] = pp_cmul(r[i], z[i]);                       // FFK *= cp      (:419)
+                    part = pp_acc(part, r[i].x, r[i].y, A[i], B[i]);  // TK[itau] += FFK (:420), both signs of w
+                }
+                pp_park<PP_THREADS / 32>(part, buf, b);
+            }
+#pragma unroll
+            for (int i = 0; i < PP_PER; ++i) Rb[i][tid] = pp_cmul(Rb[i][tid], Z64[i][tid]);
+            pp_commit<PP_THREADS / 32>(p, buf, k, tb0, pass > 0, pass == 0);
+        }
+    }
+}
+
+// ---- layered v(tau) (:439-487): cumulative phase in fp64 turns (reduced mod 1), one sqrt + sincos per pair and tau
+__global__ void __launch_bounds__(PP_THREADS, 2) phsh_layered_pair_kernel(const __grid_constant__ PhshParams p) {
+    __shared__ float2 buf[PS_TB][PP_THREADS / 32];
+    __shared__ double sv2[PS_TB], sth[PS_TB];
+    const int tid = threadIdx.x;
+    const int k = blockIdx.x;
+    const int nh = max(1, p.nt / 2);
+    const double kx = ps_kx(k, p.T, p.dx);
+    // pairs with coss(tau = 0) <= thr2(0) are dead from the start (the mask is sticky, :484-485)
+    int s_first = 0;
+    {
+        const double v0 = p.vmig[0], th0 = p.thr2[0];
+        if (th0 < 1.0) {
+            const double wmin = 0.5 * kx * fabs(v0) / sqrt(1.0 - th0);   // coss > th0  <=>  |w| > wmin
+            s_first = (int)fmin((double)nh, floor(wmin * (double)p.nt * p.dt * 0.15915494309189535)) - 1;
+            if (s_first < 0) s_first = 0;
+        }
+    }
+    int pass = 0;
+    for (int base = s_first; base < nh || pass == 0; base += PP_STATES, ++pass) {
+        float2 A[PP_PER], B[PP_PER];
+        double c[PP_PER], wt[PP_PER], ph[PP_PER];
+        float plo[PP_PER];
+#pragma unroll
+        for (int i = 0; i < PP_PER; ++i) {
+            const int s = base + tid + i * PP_THREADS;
+            A[i] = make_float2(0.f, 0.f);
+            B[i] = A[i];
+            c[i] = 1e300;  // dead
+            wt[i] = 0.0;
+            ph[i] = 0.0;
+            plo[i] = 0.f;
+            if (s < nh) {
+                const double w = ps_omega(s, p.nt, p.dt);
+                const double h = 0.5 * kx / w;
+                c[i] = h * h;                                // coss = 1 - c * v^2   (:460)
+                wt[i] = w * p.dt * 0.15915494309189535;      // phase advance in turns per unit sqrt(coss), < 0.5
+                pp_load_pair(p, s, k, A[i], B[i]);
+            }
+        }
+        for (int tb0 = 0; tb0 < p.S; tb0 += PS_TB) {
+            const int nb = min(PS_TB, p.S - tb0);
+            if (tid < nb) {
+                const double v = p.vmig[tb0 + tid];
+                sv2[tid] = v * v;
+                sth[tid] = p.thr2[tb0 + tid];
+            }
+            __syncthreads();
+            for (int b = 0; b < nb; ++b) {
+                const double v2 = sv2[b], th = sth[b];
+                float2 part = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < PP_PER; ++i) {
+                    const double coss = fma(-c[i], v2, 1.0);
+                    if (coss <= th) {  // evanescent from here on (:484-485, sticky because FK itself is zeroed)
+                        c[i] = 1e300;
+                    } else {
+                        // sqrt(coss) = s0 + e / (2 s0): fp32 rsqrt seed, fp64 residual; the small correction term is
+                        // accumulated in fp32 next to the fp64 phase
+                        const float cf = (float)coss;
+                        float rs;
+                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(cf));
+                        const float s0 = cf * rs;
+                        const double s0d = (double)s0;
+                        const float ef = (float)fma(-s0d, s0d, coss);
+                        double phn = fma(wt[i], s0d, ph[i]);
+                        if (phn > 0.5) phn -= 1.0;
+                        ph[i] = phn;
+                        plo[i] = fmaf((float)wt[i] * ef, 0.5f * rs, plo[i]);
+                        float sn, cs;
+                        __sincosf(((float)phn + plo[i]) * 6.283185307179586f, &sn, &cs);
+                        part = pp_acc(part, cs, sn, A[i], B[i]);
+                    }
+                }
+                pp_park<PP_THREADS / 32>(part, buf, b);
+            }
+            pp_commit<PP_THREADS / 32>(p, buf, k, tb0, pass > 0, false);
+        }
+    }
+}
+
+// The unpaired Nyquist-frequency bin of the layered case: FK[nt/2, k] cos(cumulative phase), one thread per kx.
+__global__ void __launch_bounds__(128) phsh_layered_nyq_kernel(const __grid_constant__ PhshParams p) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p.K || p.nt < 2) return;
+    const double w = ps_omega(p.nt / 2, p.nt, p.dt);
+    const double h = 0.5 * ps_kx(k, p.T, p.dx) / w;
+    const double c = h * h, wt = w * p.dt * 0.15915494309189535;
+    const float2 f = p.FK[(size_t)(p.nt / 2) * p.K + k];
+    double ph = 0.0;
+    for (int tau = 0; tau < p.S; ++tau) {
+        const double v = p.vmig[tau];
+        const double coss = fma(-c, v * v, 1.0);
+        if (coss <= p.thr2[tau]) break;
+        ph = fma(wt, sqrt(coss), ph);
+        ph -= rint(ph);
+        const float cs = (float)cospi(2.0 * ph);
+        float2 *dst = p.TK + (size_t)tau * p.K + k;
+        float2 o = *dst;
+        o.x = fmaf(f.x * cs, p.inv_s, o.x);
+        o.y = fmaf(f.y * cs, p.inv_s, o.y);
+        *dst = o;
+    }
+}
+
+static int g_phsh_legacy = 0;  // testing hook: 1 = the one-bin-per-state kernels
+
 struct PhshPlans {
     cufftHandle r2c = 0, c2c = 0, c2r = 0;
 };
@@ -289,11 +539,6 @@ static inline int ps_next_pow2(int S) {
     int nt = 1;
     while (nt < S) nt <<= 1;
     return nt;
-}
-
-__global__ void scale_kernel(float *x, size_t n, float s) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        x[i] *= s;
 }
 
 }  // namespace impdar
@@ -347,7 +592,21 @@ int impdar_phsh_f32(const float *data, float *out, int S, int T, double dt, doub
     PhshParams p;
     p.FK = FK; p.TK = TK; p.nt = nt; p.K = K; p.S = S; p.T = T;
     p.dt = dt; p.dx = fabs(dx); p.vel = vel; p.vmig = vmig; p.thr2 = thr2;
-    p.inv_s = (float)(1.0 / (double)S);
+    p.inv_s = (float)(1.0 / ((double)S * (double)T));  // /snum (:490-492) and numpy ifft's 1/tnum (:282)
+    if (!g_phsh_legacy) {
+        if (vmig == nullptr) {
+            phsh_const_pair_kernel<<<K, PP_THREADS, 0, st>>>(p);
+            IMPDAR_LAUNCH_CHECK();
+        } else {
+            phsh_layered_pair_kernel<<<K, PP_THREADS, 0, st>>>(p);
+            IMPDAR_LAUNCH_CHECK();
+            phsh_layered_nyq_kernel<<<(K + 127) / 128, 128, 0, st>>>(p);
+            IMPDAR_LAUNCH_CHECK();
+        }
+        IMPDAR_CUFFT(cufftExecC2R(pl.c2r, (cufftComplex *)TK, out));  // kx -> x
+        count_launch(1);
+        return IMPDAR_B200_OK;
+    }
     if (vmig == nullptr) {
         const size_t smem = 2 * (size_t)PSC_PER * PS_THREADS * sizeof(float2);
         IMPDAR_CUDA(cudaFuncSetAttribute(phsh_const_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -358,9 +617,11 @@ int impdar_phsh_f32(const float *data, float *out, int S, int T, double dt, doub
     IMPDAR_LAUNCH_CHECK();
     IMPDAR_CUFFT(cufftExecC2R(pl.c2r, (cufftComplex *)TK, out));  // kx -> x (unnormalised)
     count_launch(1);
-    const size_t n = (size_t)S * T;
-    scale_kernel<<<num_sms() * 8, 256, 0, st>>>(out, n, (float)(1.0 / (double)T));  // numpy ifft's 1/T
-    IMPDAR_LAUNCH_CHECK();
+    return IMPDAR_B200_OK;
+}
+
+int impdar_phsh_set_legacy(int on) {
+    g_phsh_legacy = on ? 1 : 0;
     return IMPDAR_B200_OK;
 }
 

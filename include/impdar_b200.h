@@ -152,6 +152,9 @@ int impdar_phsh_f32(const float *data, float *out, int snum, int tnum, double dt
                     const double *vmig, const double *thr2, double htaper, double vtaper,
                     void *workspace, size_t workspace_bytes, void *stream);
 
+/* Testing hook: 1 selects the one-frequency-bin-per-state kernels instead of the (+w, -w) pair kernels. */
+int impdar_phsh_set_legacy(int on);
+
 #ifdef __cplusplus
 }
 #endif
