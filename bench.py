@@ -98,6 +98,53 @@ class ClockSampler(object):
         return out
 
 
+# ------------------------------------------------------------------------------ per-kernel timing
+def kernel_times(names):
+    """{kernel: (avg ms per launch, launches)} from the library's CUDA-event brackets (recorded on the stream
+    the kernel is launched on, inside the timed region)."""
+    import ctypes
+    from impdar_b200 import _lib
+    lib = _lib.load()
+    out = {}
+    for n in names:
+        ms, cnt = ctypes.c_double(0.0), ctypes.c_int(0)
+        _lib.check(lib.impdar_b200_kernel_timer_read(n.encode(), ctypes.byref(ms), ctypes.byref(cnt)))
+        if cnt.value:
+            out[n] = (ms.value / cnt.value, cnt.value)
+    return out
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/traffic.json,
+    written by scripts/ncu_summary.py), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    return d.get(kernel, {}).get("dram_bytes")
+
+
+def hbm_kernel_roofline(wl, table, ms_step, bytes_per_sample_step, hbm_gbs):
+    """HBM-bound paths: `table` = {kernel: algorithmic bytes per launch}.  The dominant kernel (largest total time
+    in the timed region) gives achieved/peak/frac; the whole step on SURVEY 8d's byte model is reported beside it."""
+    kt = kernel_times(list(table))
+    step_gbs = wl.units * bytes_per_sample_step / (ms_step * 1e-3) / 1e9
+    r = {"bound": "hbm", "peak": hbm_gbs, "unit": "GB/s", "step_bytes_per_sample": bytes_per_sample_step,
+         "step_achieved": step_gbs, "step_frac": step_gbs / hbm_gbs}
+    if not kt:
+        r.update({"achieved": step_gbs, "frac": step_gbs / hbm_gbs, "traffic": None, "kernel": "whole step"})
+        return r
+    dom = max(kt, key=lambda k: kt[k][0] * kt[k][1])
+    ms, cnt = kt[dom]
+    gbs = table[dom] / (ms * 1e-3) / 1e9
+    r.update({"achieved": gbs, "frac": gbs / hbm_gbs, "kernel": dom, "kernel_ms": ms, "kernel_launches": cnt,
+              "algorithmic_bytes_per_launch": table[dom], "traffic": ncu_traffic(dom),
+              "kernel_share_of_step": ms * cnt / (ms_step * wl.args.steps),
+              "kernels": {k: {"ms": v[0], "launches": v[1], "GBps": table[k] / (v[0] * 1e-3) / 1e9} for k, v in kt.items()}})
+    return r
+
+
 # --------------------------------------------------------------------------------------- workloads
 class Workload(object):
     name = ""
@@ -153,12 +200,17 @@ class KirchhoffC2(Workload):
         # compulsory HBM traffic (8 B/sample) are reported beside it.
         from impdar_b200 import migrationlib as ml
         path = ml.kirchhoff_last_path()
-        pairs_s = self.pairs / (ms * 1e-3)
+        kname = "kirch_table_kernel" if path == "table" else "kirch_general_kernel"
+        kt = kernel_times([kname])
+        kms, kcnt = kt.get(kname, (ms, self.args.steps))
+        pairs_s = self.pairs / (kms * 1e-3)
         hbm = self.units * 8 / (ms * 1e-3) / 1e9
         peak = 148 * 32 * 1.965e9 / 2.0 if path == "table" else 148 * 128 * 1.965e9 / 18.0
         return {"bound": "l1_load_wavefronts" if path == "table" else "sm_issue", "achieved": pairs_s, "peak": peak,
-                "unit": "pair/s", "frac": pairs_s / peak, "traffic": None,
-                "kernel": "kirch_table_kernel" if path == "table" else "kirch_general_kernel",
+                "unit": "pair/s", "frac": pairs_s / peak, "traffic": ncu_traffic(kname),
+                "kernel": kname, "kernel_ms": kms, "kernel_launches": kcnt,
+                "kernel_share_of_step": kms * kcnt / (ms * self.args.steps),
+                "step_pairs_per_s": self.pairs / (ms * 1e-3),
                 "peak_model": ("one misaligned 128B L1 load per 32 pairs = 2 wavefronts/SM/clk" if path == "table"
                                else "18 issue slots per pair (measured SASS: 23)"),
                 "survey_issue_model_peak": 4.0e12, "frac_of_survey_model": pairs_s / 4.0e12,
@@ -176,7 +228,7 @@ class KirchhoffC2(Workload):
         return time.perf_counter() - t0, n_samples
 
     cpu_sample_desc = "oracle.migration.kirchhoff_loops: %d output samples of trace tnum/2 against the full 2048x4096 input"
-    cpu_default_n = 64
+    cpu_default_n = 160
 
 
 class KirchhoffC5(KirchhoffC2):
@@ -200,9 +252,8 @@ class KirchhoffC5(KirchhoffC2):
         self.units = self.S * self.T / self.world   # per rank share; value is whole-job
         self.parallel = parallel
         self.xb, self.xe = parallel.kirchhoff_output_range(self.T, self.rank, self.world, self.tt, self.dist, VEL_K)
-        self.pairs = None
-        self.exact_pairs = None
         self.host = None
+        self.count_pairs()
 
     def step(self):
         self.result = self.parallel.kirchhoff_sharded_device(self.x, self.tt, self.dist, VEL_K, False,
@@ -211,14 +262,39 @@ class KirchhoffC5(KirchhoffC2):
     def e2e_step(self):
         return None
 
+    def count_pairs(self):
+        """(sample, trace) pairs inside the aperture, counted by the kernel itself over this rank's output range and
+        summed over ranks (one extra untimed step)."""
+        import torch
+        import torch.distributed as dist
+        from impdar_b200 import migrationlib as ml
+        ml.enable_kirchhoff_stats(True)
+        self.parallel.kirchhoff_sharded_device(self.x, self.tt, self.dist, VEL_K, False, rank=self.rank,
+                                               world=self.world, gather=False)
+        torch.cuda.synchronize()
+        pairs, exact = ml.kirchhoff_stats()
+        ml.enable_kirchhoff_stats(False)
+        t = torch.tensor([float(pairs), float(exact)], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(t)
+        self.pairs, self.exact_pairs = float(t[0].item()), float(t[1].item())
+
     def roofline(self, ms, hbm_gbs, src):
-        from oracle import migration as om
-        if self.pairs is None:
-            self.pairs = om.kirchhoff_pair_count(self.tt, self.dist, VEL_K)
-        pairs_s = self.pairs / (ms * 1e-3)
-        return {"bound": "sm_issue", "achieved": pairs_s, "peak": 4.0e12 * self.world, "unit": "pair/s",
-                "frac": pairs_s / (4.0e12 * self.world), "traffic": None, "kernel": "kirch_general_kernel",
-                "pairs_per_launch": self.pairs}
+        from impdar_b200 import migrationlib as ml
+        path = ml.kirchhoff_last_path()
+        kname = "kirch_table_kernel" if path == "table" else "kirch_general_kernel"
+        kt = kernel_times([kname])
+        kms, kcnt = kt.get(kname, (ms, self.args.steps))
+        peak1 = 148 * 32 * 1.965e9 / 2.0 if path == "table" else 148 * 128 * 1.965e9 / 18.0
+        # rank 0's kernel time with rank 0's share of the pairs (ranges are balanced by pair count)
+        pairs_s = self.pairs / self.world / (kms * 1e-3)
+        return {"bound": "l1_load_wavefronts" if path == "table" else "sm_issue", "achieved": pairs_s, "peak": peak1,
+                "unit": "pair/s", "frac": pairs_s / peak1, "traffic": ncu_traffic(kname), "kernel": kname,
+                "kernel_ms": kms, "kernel_launches": kcnt, "kernel_share_of_step": kms * kcnt / (ms * self.args.steps),
+                "pairs_whole_image": self.pairs, "exact_fp64_pairs": self.exact_pairs,
+                "step_pairs_per_s_all_ranks": self.pairs / (ms * 1e-3),
+                "note": "achieved/peak are per GPU (rank 0's kernel, 1/world of the pairs); the step adds the NCCL "
+                        "broadcast of the input and the all_gather of the output blocks"}
 
 
 class StoltC5(Workload):
@@ -252,22 +328,29 @@ class StoltC5(Workload):
         return self.S * self.T * 4, d.data.nbytes, float(d.data[self.S // 2, self.T // 2])
 
     def roofline(self, ms, hbm_gbs, src):
-        gbs = self.units * 40 / (ms * 1e-3) / 1e9   # 40 B per real sample, five sweeps
-        return {"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs,
-                "traffic": None, "kernel": "whole Stolt step: taper + 2-D C2C (cuFFT) + stolt_remap_paired_kernel + 2-D C2C",
-                "bytes_per_sample": 40, "compulsory_8B_gbs": self.units * 8 / (ms * 1e-3) / 1e9}
+        # 40 B per real sample = five sweeps that each read and write the (paired-trace complex)
+        # image once: rowA fwd (+taper), rowB fwd (+transpose), col (FFT_t, remap, iFFT_t), rowB inv, rowA inv.
+        # Every pass kernel therefore moves 8 B per real sample per launch (algorithmic bytes).
+        per = float(self.units) * 8
+        table = {"stolt_col_kernel": per, "stolt_rowA_kernel": per, "stolt_rowB_kernel": per,
+                 "stolt_remap_paired_kernel": per, "stolt_remap_kernel": per}
+        r = hbm_kernel_roofline(self, table, ms, 40, hbm_gbs)
+        r["compulsory_8B_gbs"] = self.units * 8 / (ms * 1e-3) / 1e9
+        return r
 
     def cpu_sample(self, n, xi=None):
         from oracle import migration as om
-        S, T = 512, 1024   # bounded sample: same per-cell cost (two FITPACK point evaluations per (kz, kx) cell)
+        S, T = 1024, 2048   # bounded sample: same per-cell cost (two FITPACK point evaluations per (kz, kx) cell)
         img = self.x if self.x.dim() == 2 else self.x[0]
         x64 = img[:S, :T].double().cpu().numpy()
+        stride = max(1, 512 // n)
+        rows = len(range(0, S // 2, stride))
         t0 = time.perf_counter()
-        om.stolt_loops(x64, 1e-8, np.ones(T) * 5.0, np.arange(T) * 0.005, VEL_S, 10, 10, row_stride=max(1, 256 // n))
-        return time.perf_counter() - t0, S * T * n / 256.0
+        om.stolt_loops(x64, 1e-8, np.ones(T) * 5.0, np.arange(T) * 0.005, VEL_S, 10, 10, row_stride=stride)
+        return time.perf_counter() - t0, S * T * rows / 512.0
 
-    cpu_sample_desc = "oracle.migration.stolt_loops (FITPACK point evaluation per cell) on %d/256 of the kz rows of a 512x1024 crop"
-    cpu_default_n = 64
+    cpu_sample_desc = "oracle.migration.stolt_loops (FITPACK point evaluation per cell) on ~%d of the 512 kz rows of a 1024x2048 crop"
+    cpu_default_n = 256
 
 
 class StoltC4(StoltC5):
@@ -322,9 +405,11 @@ class PipelineC4(Workload):
     e2e_units = 2048 * 8192
 
     def roofline(self, ms, hbm_gbs, src):
-        gbs = self.units * 56 / (ms * 1e-3) / 1e9   # 8 + 8 + 40 B/sample unfused
-        return {"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs,
-                "traffic": None, "kernel": "whole pipeline step (filtfilt + hfilt + Stolt)", "bytes_per_sample": 56}
+        # 8 + 8 + 40 B/sample unfused; every kernel of the step moves 8 B/sample algorithmically
+        per = float(self.units) * 8
+        table = {"filtfilt_kernel": per, "hfilt_kernel": per, "stolt_col_kernel": per, "stolt_rowA_kernel": per,
+                 "stolt_rowB_kernel": per, "stolt_remap_paired_kernel": per}
+        return hbm_kernel_roofline(self, table, ms, 56, hbm_gbs)
 
     def cpu_sample(self, n, xi=None):
         from oracle import filtering as of
@@ -340,9 +425,9 @@ class PipelineC4(Workload):
         elapsed = t_f + t_s
         return elapsed, self.S * self.T * elapsed / t_full
 
-    cpu_sample_desc = ("oracle vertical_band_pass + horizontalfilt on one full profile (measured) + stolt_loops on %d/256 "
-                       "of the rows of a 512x1024 crop extrapolated by cell count to the profile")
-    cpu_default_n = 32
+    cpu_sample_desc = ("oracle vertical_band_pass + horizontalfilt on one full profile (measured) + stolt_loops on ~%d of the "
+                       "512 kz rows of a 1024x2048 crop extrapolated by cell count to the profile")
+    cpu_default_n = 128
 
 
 class PhshC3(Workload):
@@ -388,9 +473,14 @@ class PhshC3(Workload):
         peak = 148 * 128 * 1.965e9 / 6.0   # 6 FP32 issue slots per complex multiply-accumulate
         if self.layered:
             peak = 148 * 16 * 1.965e9 / 3.0   # MUFU bound: rsqrt + sin + cos per (tau, w, k)
-        return {"bound": "fp32_simt" if not self.layered else "mufu", "achieved": macs / (ms * 1e-3), "peak": peak,
-                "unit": "cmac/s", "frac": macs / (ms * 1e-3) / peak, "traffic": None,
-                "kernel": "phsh_layered_kernel" if self.layered else "phsh_const_kernel"}
+        kname = "phsh_layered_pair_kernel" if self.layered else "phsh_const_pair_kernel"
+        kt = kernel_times([kname])
+        kms, kcnt = kt.get(kname, (ms, self.args.steps))
+        return {"bound": "fp32_simt" if not self.layered else "mufu", "achieved": macs / (kms * 1e-3), "peak": peak,
+                "unit": "cmac/s", "frac": macs / (kms * 1e-3) / peak, "traffic": ncu_traffic(kname),
+                "kernel": kname, "kernel_ms": kms, "kernel_launches": kcnt,
+                "kernel_share_of_step": kms * kcnt / (ms * self.args.steps),
+                "cmacs_per_launch": macs}
 
     def cpu_sample(self, n, xi=None):
         from oracle import migration as om
@@ -406,7 +496,7 @@ class PhshC3(Workload):
         return time.perf_counter() - t0, n * T
 
     cpu_sample_desc = "oracle phase-shift recurrence (vectorised over (w,kx), sequential in tau): %d taus x 256 traces, all frequencies"
-    cpu_default_n = 16
+    cpu_default_n = 256
 
 
 class PhshC3Layered(PhshC3):
@@ -550,6 +640,7 @@ def main():
         sampler.start()
     launches0 = lib.impdar_b200_launch_count()
     evs = []
+    lib.impdar_b200_kernel_timer(1)   # CUDA-event brackets around the dominant kernels, on their launch stream
     barrier()
     torch.cuda.profiler.start()   # ncu --profile-from-start off captures only the timed region
     for _ in range(args.steps):
@@ -563,6 +654,7 @@ def main():
         evs.append((a, b))
     barrier()
     torch.cuda.profiler.stop()
+    lib.impdar_b200_kernel_timer(0)   # stop recording; the records stay readable for roofline()
     launches = lib.impdar_b200_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     total_ms = sum(a.elapsed_time(b) for a, b in evs)

@@ -19,6 +19,8 @@ PROTOTYPES = {
     "impdar_b200_version": (_c_int, []),
     "impdar_b200_last_error": (ctypes.c_char_p, []),
     "impdar_b200_launch_count": (ctypes.c_ulonglong, []),
+    "impdar_b200_kernel_timer": (_c_int, [_c_int]),
+    "impdar_b200_kernel_timer_read": (_c_int, [ctypes.c_char_p, _vp, _vp]),
     "impdar_taper_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_int, _vp]),
     "impdar_hfilt_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
     "impdar_hfilt_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),

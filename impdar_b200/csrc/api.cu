@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -21,6 +22,41 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// ---- per-kernel CUDA-event timer (off by default; bench.py switches it on for the timed region)
+struct KtRec {
+    const char *name;
+    cudaEvent_t a, b;
+};
+static std::atomic<int> g_kt_on{0};
+static std::mutex g_kt_mu;
+static std::vector<KtRec> g_kt;
+static thread_local KtRec g_kt_open = {nullptr, nullptr, nullptr};
+
+void ktimer_begin(const char *kernel, cudaStream_t st) {
+    if (!g_kt_on.load(std::memory_order_relaxed)) return;
+    KtRec r = {kernel, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    g_kt_open = r;
+}
+void ktimer_end(cudaStream_t st) {
+    if (!g_kt_open.name) return;
+    cudaEventRecord(g_kt_open.b, st);
+    {
+        std::lock_guard<std::mutex> lk(g_kt_mu);
+        g_kt.push_back(g_kt_open);
+    }
+    g_kt_open.name = nullptr;
+}
+static void ktimer_clear() {
+    std::lock_guard<std::mutex> lk(g_kt_mu);
+    for (auto &r : g_kt) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_kt.clear();
+}
 
 // np.gradient(f, x, axis=0) stencil rows a, b, c (numpy/lib/_function_base_impl.py gradient, edge_order=1):
 // uniform spacing (all diffs equal) -> central difference over 2h that never touches f[i]; otherwise the
@@ -101,6 +137,30 @@ extern "C" {
 int impdar_b200_version(void) { return 100; }
 const char *impdar_b200_last_error(void) { return g_err; }
 unsigned long long impdar_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int impdar_b200_kernel_timer(int on) {
+    const int prev = g_kt_on.exchange(on ? 1 : 0);
+    if (on) ktimer_clear();
+    return prev;
+}
+
+int impdar_b200_kernel_timer_read(const char *kernel, double *total_ms, int *launches) {
+    IMPDAR_CHECK_ARG(total_ms && launches, "kernel_timer_read: null pointer");
+    double tot = 0.0;
+    int n = 0;
+    std::lock_guard<std::mutex> lk(g_kt_mu);
+    for (auto &r : g_kt) {
+        if (kernel && strcmp(kernel, r.name) != 0) continue;
+        IMPDAR_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        IMPDAR_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        tot += ms;
+        ++n;
+    }
+    *total_ms = tot;
+    *launches = n;
+    return IMPDAR_B200_OK;
+}
 
 int impdar_kirchhoff_host_f64(const double *data, double *migdata, int S, int T, const double *dist_m,
                               const double *tt_s, double vel, int nearfield) {

@@ -11,6 +11,10 @@ namespace impdar {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+// Optional CUDA-event bracket around one kernel launch (impdar_b200_kernel_timer, for bench.py's roofline:
+// the dominant kernel's own duration on the stream it is launched on).  No-ops unless enabled.
+void ktimer_begin(const char *kernel, cudaStream_t st);
+void ktimer_end(cudaStream_t st);
 
 #define IMPDAR_CHECK_ARG(cond, ...)            \
     do {                                       \

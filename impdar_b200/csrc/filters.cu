@@ -488,7 +488,9 @@ static int launch_filtfilt(const T *x, T *y, T *work, int S, int Tn, int batch, 
     // one trace per thread: small problems use one warp per CTA so that every SM gets work
     const int block = (ntraces < (long long)num_sms() * 64 * 2) ? 32 : 64;
     const long long grid = (ntraces + block - 1) / block;
+    ktimer_begin("filtfilt_kernel", st);
     filtfilt_kernel<T, NS><<<(unsigned)grid, block, 0, st>>>(x, y, work, S, Tn, ntraces, padlen, c);
+    ktimer_end(st);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
 }
@@ -571,8 +573,10 @@ static int hfilt_impl(const T *x, T *y, int S, int Tn, int batch, int htr1, int 
     long long grid = rows;
     const long long cap = (long long)num_sms() * 32;
     if (grid > cap) grid = cap;
+    ktimer_begin("hfilt_kernel", (cudaStream_t)stream);
     hfilt_kernel<T><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, y, S, Tn, rows, htr1, htrn, taper,
                                                                      trunc_avg);
+    ktimer_end((cudaStream_t)stream);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
 }
@@ -622,7 +626,9 @@ static int ahfilt_impl(const T *x, T *y, int S, int Tn, int batch, int w, const 
             const int R = 64;
             dim3 grid((Tn + W - 1) / W, (S + R - 1) / R, batch);
             IMPDAR_CHECK_ARG(batch <= 65535 && grid.y <= 65535, "ahfilt: batch too large");
+            ktimer_begin("ahfilt_strip_kernel", (cudaStream_t)stream);
             ahfilt_strip_kernel<T><<<grid, 256, smem_strip, (cudaStream_t)stream>>>(x, y, S, Tn, w, tail_lo, taper, W, R);
+            ktimer_end((cudaStream_t)stream);
             IMPDAR_LAUNCH_CHECK();
             return IMPDAR_B200_OK;
         }
@@ -646,8 +652,10 @@ static int ahfilt_impl(const T *x, T *y, int S, int Tn, int batch, int w, const 
             IMPDAR_CUDA(cudaFuncSetAttribute(ahfilt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
     }
+    ktimer_begin("ahfilt_kernel", (cudaStream_t)stream);
     ahfilt_kernel<T><<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(x, y, S, Tn, rows, w, tail_lo, taper,
                                                                          scratch);
+    ktimer_end((cudaStream_t)stream);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
 }

@@ -710,11 +710,11 @@ int impdar_kirchhoff_f32(const float *data, float *out, int S, int T, const doub
         tp.x_begin = x_begin; tp.x_end = x_end;
         dim3 grid(S, (x_end - x_begin + 4 * 32 * KT_R - 1) / (4 * 32 * KT_R));
         if (g_stats_enabled) {
-            if (nearfield) kirch_table_kernel<true, true><<<grid, 128, 0, st>>>(tp);
-            else kirch_table_kernel<false, true><<<grid, 128, 0, st>>>(tp);
+            if (nearfield) { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<true, true><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
+            else { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<false, true><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
         } else {
-            if (nearfield) kirch_table_kernel<true, false><<<grid, 128, 0, st>>>(tp);
-            else kirch_table_kernel<false, false><<<grid, 128, 0, st>>>(tp);
+            if (nearfield) { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<true, false><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
+            else { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<false, false><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
         }
         IMPDAR_LAUNCH_CHECK();
         // exact pass over flagged table entries (reads the same padded row-major images)
@@ -743,11 +743,11 @@ int impdar_kirchhoff_f32(const float *data, float *out, int S, int T, const doub
         p.gradT = gradT; p.dataT = dataT; p.SP = SP;
         dim3 grid((S + 31) / 32, (x_end - x_begin + 7) / 8), block(32, 8);
         if (g_stats_enabled) {
-            if (nearfield) kirch_general_kernel<true, true><<<grid, block, 0, st>>>(p);
-            else kirch_general_kernel<false, true><<<grid, block, 0, st>>>(p);
+            if (nearfield) { ktimer_begin("kirch_general_kernel", st); kirch_general_kernel<true, true><<<grid, block, 0, st>>>(p); ktimer_end(st); }
+            else { ktimer_begin("kirch_general_kernel", st); kirch_general_kernel<false, true><<<grid, block, 0, st>>>(p); ktimer_end(st); }
         } else {
-            if (nearfield) kirch_general_kernel<true, false><<<grid, block, 0, st>>>(p);
-            else kirch_general_kernel<false, false><<<grid, block, 0, st>>>(p);
+            if (nearfield) { ktimer_begin("kirch_general_kernel", st); kirch_general_kernel<true, false><<<grid, block, 0, st>>>(p); ktimer_end(st); }
+            else { ktimer_begin("kirch_general_kernel", st); kirch_general_kernel<false, false><<<grid, block, 0, st>>>(p); ktimer_end(st); }
         }
         IMPDAR_LAUNCH_CHECK();
     }

@@ -595,10 +595,14 @@ int impdar_phsh_f32(const float *data, float *out, int S, int T, double dt, doub
     p.inv_s = (float)(1.0 / ((double)S * (double)T));  // /snum (:490-492) and numpy ifft's 1/tnum (:282)
     if (!g_phsh_legacy) {
         if (vmig == nullptr) {
+            ktimer_begin("phsh_const_pair_kernel", st);
             phsh_const_pair_kernel<<<K, PP_THREADS, 0, st>>>(p);
+            ktimer_end(st);
             IMPDAR_LAUNCH_CHECK();
         } else {
+            ktimer_begin("phsh_layered_pair_kernel", st);
             phsh_layered_pair_kernel<<<K, PP_THREADS, 0, st>>>(p);
+            ktimer_end(st);
             IMPDAR_LAUNCH_CHECK();
             phsh_layered_nyq_kernel<<<(K + 127) / 128, 128, 0, st>>>(p);
             IMPDAR_LAUNCH_CHECK();
@@ -610,9 +614,13 @@ int impdar_phsh_f32(const float *data, float *out, int S, int T, double dt, doub
     if (vmig == nullptr) {
         const size_t smem = 2 * (size_t)PSC_PER * PS_THREADS * sizeof(float2);
         IMPDAR_CUDA(cudaFuncSetAttribute(phsh_const_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ktimer_begin("phsh_const_kernel", st);
         phsh_const_kernel<<<(K + PSC_COLS - 1) / PSC_COLS, PS_THREADS, smem, st>>>(p);
+        ktimer_end(st);
     } else {
+        ktimer_begin("phsh_layered_kernel", st);
         phsh_layered_kernel<<<K, PS_THREADS, 0, st>>>(p);
+        ktimer_end(st);
     }
     IMPDAR_LAUNCH_CHECK();
     IMPDAR_CUFFT(cufftExecC2R(pl.c2r, (cufftComplex *)TK, out));  // kx -> x (unnormalised)

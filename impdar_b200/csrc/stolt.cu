@@ -315,7 +315,9 @@ int impdar_stolt_f32(const float *data, float *out, int S, int T, int batch, dou
             pp.Zq = (float2 *)dout;
             const int rows_per_cta = 32;
             dim3 grid((pp.Th + 127) / 128, (pp.nz + rows_per_cta - 1) / rows_per_cta);
+            ktimer_begin("stolt_remap_paired_kernel", st);
             stolt_remap_paired_kernel<<<grid, 128, 0, st>>>(pp, rows_per_cta);
+            ktimer_end(st);
             IMPDAR_LAUNCH_CHECK();
             IMPDAR_CUFFT(cufftExecC2C(pl.c2c2d, (cufftComplex *)dout, (cufftComplex *)dout, CUFFT_INVERSE));
             count_launch(2);
@@ -344,7 +346,9 @@ int impdar_stolt_f32(const float *data, float *out, int S, int T, int batch, dou
         rp.KK = bufKK;
         const int rows_per_cta = 32;
         dim3 grid((T + 127) / 128, (M + rows_per_cta - 1) / rows_per_cta);
+        ktimer_begin("stolt_remap_kernel", st);
         stolt_remap_kernel<<<grid, 128, 0, st>>>(rp, rows_per_cta);
+        ktimer_end(st);
         IMPDAR_LAUNCH_CHECK();
         IMPDAR_CUFFT(cufftExecC2C(pl.c2c, (cufftComplex *)bufKK, (cufftComplex *)bufKK, CUFFT_INVERSE));
         IMPDAR_CUFFT(cufftExecC2R(pl.c2r, (cufftComplex *)bufKK, dout));

@@ -724,7 +724,9 @@ static int launch_rowA(const RowAParams &p, cudaStream_t st) {
         attr_done = true;
     }
     dim3 grid(N2 / NC2, (p.S + p.rows_per_cta - 1) / p.rows_per_cta, p.batch);
+    ktimer_begin("stolt_rowA_kernel", st);
     stolt_rowA_kernel<N1, DIR><<<grid, 256, smem, st>>>(p);
+    ktimer_end(st);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
 }
@@ -752,10 +754,14 @@ static int launch_rowB(const RowBParams &p, cudaStream_t st) {
         attr_done = true;
     }
     dim3 grid(p.N1 / 2 - 1, p.S / 16, p.batch);
+    ktimer_begin("stolt_rowB_kernel", st);
     stolt_rowB_kernel<DIR><<<grid, 256, smem, st>>>(p);
+    ktimer_end(st);
     IMPDAR_LAUNCH_CHECK();
     dim3 grid_self(2, p.S / 16, p.batch);  // k1 = 0 and k1 = N1/2
+    ktimer_begin("stolt_rowB_self_kernel", st);
     stolt_rowB_self_kernel<DIR><<<grid_self, 256, smem, st>>>(p);
+    ktimer_end(st);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
 }
@@ -773,7 +779,9 @@ static int launch_col(const ColParams &p, cudaStream_t st) {
     }
     int grid = num_sms() * ctas_per_sm;
     if (grid > p.ncols) grid = p.ncols;
+    ktimer_begin("stolt_col_kernel", st);
     stolt_col_kernel<S, R3><<<grid, NT, smem, st>>>(p);
+    ktimer_end(st);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
 }

@@ -41,6 +41,12 @@ int impdar_b200_version(void);
 const char *impdar_b200_last_error(void);
 /* Number of kernels launched by this library on the calling process since load (bench `gpu_launches`). */
 unsigned long long impdar_b200_launch_count(void);
+/* Measurement hook (bench.py roofline): while on, the dominant kernel of every path is bracketed by CUDA events
+ * on the stream it is launched on.  impdar_b200_kernel_timer(1) clears earlier records; returns the previous
+ * state.  _read sums the recorded launches of `kernel` (a __global__ function name such as "kirch_table_kernel";
+ * NULL = all timed kernels) and synchronises on their events.                                           */
+int impdar_b200_kernel_timer(int on);
+int impdar_b200_kernel_timer_read(const char *kernel, double *total_ms, int *launches);
 
 /* ---------------------------------------------------------------- taper (mig_python.py:152-157) --- */
 /* y = x * h[t] * v[s],  h = min(min(t, T-1-t)/htaper, 1), v likewise.  trunc_int != 0 reproduces the

@@ -1,5 +1,6 @@
 """Print the handful of ncu metrics we track from a --page raw --csv export (one row per kernel)."""
-import csv, sys
+import csv, json, os, re, sys
+# usage: ncu_summary.py raw.csv [traffic.json]   (the second argument accumulates {kernel: dram bytes per launch})
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
 keys = ['Kernel Name', 'gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
@@ -22,3 +23,19 @@ for vals in rows[2:]:
             except ValueError:
                 pass
             print(f'{h:85s} {vals[i]:>20s} {units[i]}')
+
+if len(sys.argv) > 2:
+    path = sys.argv[2]
+    tr = json.load(open(path)) if os.path.exists(path) else {}
+    mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    tmul = {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 's': 1e3}
+    col = {h: i for i, h in enumerate(hdr)}
+    for vals in rows[2:]:
+        m = re.search(r'([A-Za-z_0-9]+)\s*(<|\()', vals[col['Kernel Name']].replace('void ', '').replace('impdar::', ''))
+        if not m:
+            continue
+        def val(h, table):
+            return float(vals[col[h]].replace(',', '')) * table.get(units[col[h]], 1.0)
+        tr[m.group(1)] = {'dram_bytes': val('dram__bytes_read.sum', mult) + val('dram__bytes_write.sum', mult),
+                          'ncu_ms': val('gpu__time_duration.sum', tmul), 'source': os.path.basename(sys.argv[1])}
+    json.dump(tr, open(path, 'w'), indent=1, sort_keys=True)
