@@ -6,7 +6,7 @@
 
 or, without ImpDAR installed, ``impdar_b200.RadarData`` offers the same hot-path methods.
 """
-from . import migrationlib, filtering  # noqa: F401
+from . import migrationlib, filtering, process  # noqa: F401  (process.process mirrors impdar.lib.process.process)
 from .radardata import RadarData, RadarFlags  # noqa: F401
 from .migrationlib import (migrationKirchhoff, migrationStolt, migrationPhaseShift,  # noqa: F401
                            migrationTimeWavenumber, getVelocityProfile)

@@ -503,14 +503,14 @@ static int g_phsh_legacy = 0;  // testing hook: 1 = the one-bin-per-state kernel
 struct PhshPlans {
     cufftHandle r2c = 0, c2c = 0, c2r = 0;
 };
-static std::map<std::tuple<int, int, int, int>, PhshPlans> g_ps_plans;  // (device, S, T, nt)
+static std::map<std::tuple<int, int, int, int, long long>, PhshPlans> g_ps_plans;  // (device, S, T, nt, stream)
 static std::mutex g_ps_mu;
 
-static int ps_get_plans(int S, int T, int nt, PhshPlans &out) {
+static int ps_get_plans(int S, int T, int nt, cudaStream_t st, PhshPlans &out) {
     int dev = 0;
     IMPDAR_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_ps_mu);
-    auto key = std::make_tuple(dev, S, T, nt);
+    auto key = std::make_tuple(dev, S, T, nt, (long long)(intptr_t)st);
     auto it = g_ps_plans.find(key);
     if (it != g_ps_plans.end()) {
         out = it->second;
@@ -576,7 +576,7 @@ int impdar_phsh_f32(const float *data, float *out, int S, int T, double dt, doub
     float2 *TK = (float2 *)w2;   // ... so TK may overlay it
 
     PhshPlans pl;
-    int rc = ps_get_plans(S, T, nt, pl);
+    int rc = ps_get_plans(S, T, nt, st, pl);
     if (rc) return rc;
     IMPDAR_CUFFT(cufftSetStream(pl.r2c, st));
     IMPDAR_CUFFT(cufftSetStream(pl.c2c, st));

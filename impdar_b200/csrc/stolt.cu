@@ -180,7 +180,8 @@ struct StoltPlans {
     cufftHandle r2c = 0, c2c = 0, c2r = 0, c2c2d = 0;
     bool paired = false;
 };
-static std::map<std::tuple<int, int, int>, StoltPlans> g_plans;  // (device, S, T)
+static std::map<std::tuple<int, int, int, long long>, StoltPlans> g_plans;  // (device, S, T, stream): a cuFFT plan owns one
+// work area, so calls that may overlap on different streams get their own plans
 static std::mutex g_plans_mu;
 
 // 0 auto (five-pass kernels of stolt_fft.cu for the power-of-two shapes they cover, else the cuFFT paired-trace
@@ -197,11 +198,11 @@ size_t stolt_fft_workspace_bytes(int S, int T);
 int stolt_fft_run(const float *data, float *out, int S, int T, int batch, double dt, double dx, double vel, double htaper,
                   double vtaper, int trunc_int, void *workspace, int stop_after, cudaStream_t st);
 
-static int get_plans(int S, int T, StoltPlans &out) {
+static int get_plans(int S, int T, cudaStream_t st, StoltPlans &out) {
     int dev = 0;
     IMPDAR_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_plans_mu);
-    auto key = std::make_tuple(dev, S, stolt_use_paired(S, T) ? T : -T);
+    auto key = std::make_tuple(dev, S, stolt_use_paired(S, T) ? T : -T, (long long)(intptr_t)st);
     auto it = g_plans.find(key);
     if (it != g_plans.end()) {
         out = it->second;
@@ -296,7 +297,7 @@ int impdar_stolt_f32(const float *data, float *out, int S, int T, int batch, dou
         return IMPDAR_B200_OK;
     }
     StoltPlans pl;
-    int rc = get_plans(S, T, pl);
+    int rc = get_plans(S, T, st, pl);
     if (rc) return rc;
     g_stolt_last = pl.paired ? 2 : 1;
     if (pl.paired) {

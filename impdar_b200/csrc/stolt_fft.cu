@@ -710,6 +710,7 @@ static int get_tables(int S, int T, cudaStream_t st, Tables &out) {
     IMPDAR_LAUNCH_CHECK();
     twiddle_prod_table_kernel<<<1, 256, 0, st>>>(t.tw2);
     IMPDAR_LAUNCH_CHECK();
+    IMPDAR_CUDA(cudaStreamSynchronize(st));  // once per shape: other streams may use the tables right away
     g_tables[key] = t;
     out = t;
     return IMPDAR_B200_OK;

@@ -60,15 +60,16 @@ _workspaces = {}
 
 
 def workspace(nbytes):
-    """A cached per-device scratch buffer of at least nbytes (uint8 CUDA tensor)."""
+    """A cached scratch buffer of at least nbytes (uint8 CUDA tensor), one per (device, current stream): calls
+    enqueued on different streams (impdar_b200.process keeps several profiles in flight) never share scratch."""
     require_cuda()
-    dev = torch.cuda.current_device()
-    ws = _workspaces.get(dev)
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        _workspaces.pop(dev, None)
+        _workspaces.pop(key, None)
         ws = None
         ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device="cuda")
-        _workspaces[dev] = ws
+        _workspaces[key] = ws
     return ws
 
 
