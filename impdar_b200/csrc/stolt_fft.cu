@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(S / 32, (S >= 8192 ? 2 : (S >= 4096 ? 4 : 8)))
                 qneg = clerp(buf[padi((S - i0) & (S - 1))], w0, buf[padi(S - i0 - 1)], w1);
             } else {
                 // packed column: Z = F0 + i FN with F0 (kx = 0) and FN (kx = T/2) Hermitian in w
-                const cf zj = buf[padi(jj)], zjm = cconj(buf[padi(S - jj)]);
+                const cf zj = buf[padi(jj)], zjm = cconj(buf[padi((S - jj) & (S - 1))]);
                 const cf z0 = buf[padi(i0)], z0m = cconj(buf[padi((S - i0) & (S - 1))]);
                 const cf z1 = buf[padi(i0 + 1)], z1m = cconj(buf[padi(S - i0 - 1)]);
                 const cf q0 = cscale(cadd(zj, zjm), 0.5f * rc.norm);  // kx = 0: beta = 0, w' = w, scale 1
@@ -639,21 +639,25 @@ __global__ void __launch_bounds__(S / 32, (S >= 8192 ? 2 : (S >= 4096 ? 4 : 8)))
                 qneg = cadd(cconj(q0), cmuli(cconj(qn)));   // both Hermitian
             }
         };
-        if (tid != 0) {
+        {
+            // One code path for every thread (thread 0 owns the self-mirrored items 0 and NI/2; a separate branch for it
+            // would make warp 0 run the remap twice while the rest of the CTA waits at the barrier).  nA / nB are the
+            // mirror-row outputs of the jA / jB evaluations: element (jA, t) <-> (jB, 15 - t) in general; for thread 0
+            // (0, t) <-> (0, 16 - t) and (NI/2, t) <-> (NI/2, 15 - t), and the rows w = 0 and w = S/2 are zero.
+            const bool self = (tid == 0);
             const float fA = (float)jA, fB = (float)jB;
+            cf nA[8], nB[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                eval(jA + t * NI, fA + (float)(t * NI), vA[t], vB[15 - t]);
-                eval(jB + t * NI, fB + (float)(t * NI), vB[t], vA[15 - t]);
+                eval(jA + t * NI, fA + (float)(t * NI), vA[t], nA[t]);
+                eval(jB + t * NI, fB + (float)(t * NI), vB[t], nB[t]);
             }
-        } else {
-            // item 0: w = t NI, mirror (item 0, 16 - t); w = 0 and w = S/2 are zero.  item NI/2: mirror (same item, 15 - t)
-            vA[0] = mk(0.f, 0.f);
-            vA[8] = mk(0.f, 0.f);
 #pragma unroll
-            for (int t = 1; t < 8; ++t) eval(t * NI, (float)(t * NI), vA[t], vA[16 - t]);
+            for (int t = 0; t < 8; ++t) vB[15 - t] = self ? nB[t] : nA[t];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) eval(NI / 2 + t * NI, (float)(NI / 2 + t * NI), vB[t], vB[15 - t]);
+            for (int t = 0; t < 7; ++t) vA[15 - t] = self ? nA[t + 1] : nB[t];
+            vA[8] = self ? mk(0.f, 0.f) : nB[7];
+            if (self) vA[0] = mk(0.f, 0.f);
         }
         fft_reg<16, 1>(vA);
         fft_reg<16, 1>(vB);

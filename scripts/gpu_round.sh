@@ -5,6 +5,7 @@
 TAG=${1:-r01}
 STAGES=${2:-"tests bench quick launches full"}
 O=gpurun_out
+KEEP_REP=${KEEP_REP:-"stolt_col"}
 mkdir -p $O
 has() { [[ " $STAGES " == *" $1 "* ]]; }
 WLS="kirchhoff stolt stolt_c4 pipeline phsh phsh_layered"
@@ -36,6 +37,9 @@ cap() { # name workload regex
      -f -o $O/full_$1_$TAG python bench.py --workload $2 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $O/full_$1_$TAG.log 2>&1
   ncu -i $O/full_$1_$TAG.ncu-rep --page raw --csv > $O/full_$1_$TAG.csv 2>/dev/null
   python scripts/ncu_summary.py $O/full_$1_$TAG.csv $O/traffic_$TAG.json > $O/${TAG}_ncu_full_$1.txt 2>&1
+  ncu -i $O/full_$1_$TAG.ncu-rep --page source --csv > $O/full_$1_${TAG}_source.csv 2>/dev/null
+  # gpurun copies back at most 64 MiB: keep the reports listed in KEEP_REP only
+  [[ " $KEEP_REP " == *" $1 "* ]] || rm -f $O/full_$1_$TAG.ncu-rep
 }
 if has full; then
   cap kirch_table kirchhoff kirch_table_kernel
