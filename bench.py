@@ -118,15 +118,22 @@ def kernel_times(names):
     return out
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, kernel_ms=None):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/traffic.json,
-    written by scripts/ncu_summary.py), or None."""
+    written by scripts/ncu_summary.py), or None.  The capture is of ONE launch shape per kernel (the workload named
+    in scripts/gpu_round.sh): when the launch measured here lasts very differently from the captured one it is a
+    different shape and the figure does not apply."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
     with open(p) as f:
         d = json.load(f)
-    return d.get(kernel, {}).get("dram_bytes")
+    e = d.get(kernel)
+    if not e:
+        return None
+    if kernel_ms and e.get("ncu_ms") and not (0.6 < e["ncu_ms"] / kernel_ms < 1.6):
+        return None
+    return e.get("dram_bytes")
 
 
 def hbm_kernel_roofline(wl, table, ms_step, bytes_per_sample_step, hbm_gbs):
@@ -143,7 +150,7 @@ def hbm_kernel_roofline(wl, table, ms_step, bytes_per_sample_step, hbm_gbs):
     ms, cnt = kt[dom]
     gbs = table[dom] / (ms * 1e-3) / 1e9
     r.update({"achieved": gbs, "frac": gbs / hbm_gbs, "kernel": dom, "kernel_ms": ms, "kernel_launches": cnt,
-              "algorithmic_bytes_per_launch": table[dom], "traffic": ncu_traffic(dom),
+              "algorithmic_bytes_per_launch": table[dom], "traffic": ncu_traffic(dom, ms),
               "kernel_share_of_step": ms * cnt / (ms_step * wl.args.steps),
               "kernels": {k: {"ms": v[0], "launches": v[1], "GBps": table[k] / (v[0] * 1e-3) / 1e9} for k, v in kt.items()}})
     return r
@@ -211,7 +218,7 @@ class KirchhoffC2(Workload):
         hbm = self.units * 8 / (ms * 1e-3) / 1e9
         peak = 148 * 32 * 1.965e9 / 2.0 if path == "table" else 148 * 128 * 1.965e9 / 18.0
         return {"bound": "l1_load_wavefronts" if path == "table" else "sm_issue", "achieved": pairs_s, "peak": peak,
-                "unit": "pair/s", "frac": pairs_s / peak, "traffic": ncu_traffic(kname),
+                "unit": "pair/s", "frac": pairs_s / peak, "traffic": ncu_traffic(kname, kms),
                 "kernel": kname, "kernel_ms": kms, "kernel_launches": kcnt,
                 "kernel_share_of_step": kms * kcnt / (ms * self.args.steps),
                 "step_pairs_per_s": self.pairs / (ms * 1e-3),
@@ -293,7 +300,7 @@ class KirchhoffC5(KirchhoffC2):
         # rank 0's kernel time with rank 0's share of the pairs (ranges are balanced by pair count)
         pairs_s = self.pairs / self.world / (kms * 1e-3)
         return {"bound": "l1_load_wavefronts" if path == "table" else "sm_issue", "achieved": pairs_s, "peak": peak1,
-                "unit": "pair/s", "frac": pairs_s / peak1, "traffic": ncu_traffic(kname), "kernel": kname,
+                "unit": "pair/s", "frac": pairs_s / peak1, "traffic": ncu_traffic(kname, kms), "kernel": kname,
                 "kernel_ms": kms, "kernel_launches": kcnt, "kernel_share_of_step": kms * kcnt / (ms * self.args.steps),
                 "pairs_whole_image": self.pairs, "exact_fp64_pairs": self.exact_pairs,
                 "step_pairs_per_s_all_ranks": self.pairs / (ms * 1e-3),
@@ -483,7 +490,7 @@ class PhshC3(Workload):
         kt = kernel_times([kname])
         kms, kcnt = kt.get(kname, (ms, self.args.steps))
         return {"bound": "fp32_simt" if not self.layered else "mufu", "achieved": macs / (kms * 1e-3), "peak": peak,
-                "unit": "cmac/s", "frac": macs / (kms * 1e-3) / peak, "traffic": ncu_traffic(kname),
+                "unit": "cmac/s", "frac": macs / (kms * 1e-3) / peak, "traffic": ncu_traffic(kname, kms),
                 "kernel": kname, "kernel_ms": kms, "kernel_launches": kcnt,
                 "kernel_share_of_step": kms * kcnt / (ms * self.args.steps),
                 "cmacs_per_launch": macs}
