@@ -14,7 +14,9 @@ from .migrationlib import (migrationKirchhoff, migrationStolt, migrationPhaseShi
 __version__ = "0.1.0"
 
 _MIGRATION_NAMES = ('migrationKirchhoff', 'migrationStolt', 'migrationPhaseShift', 'migrationTimeWavenumber')
-_FILTER_NAMES = ('vertical_band_pass', 'horizontalfilt', 'adaptivehfilt')
+_FILTER_NAMES = ('vertical_band_pass', 'horizontalfilt', 'adaptivehfilt',
+                 # sibling filters on the same kernels
+                 'highpass', 'lowpass', 'horizontal_band_pass', 'winavg_hfilt', 'rangegain', 'agc')
 _saved = {}
 
 

@@ -33,6 +33,16 @@ PROTOTYPES = {
     "impdar_filtfilt_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _c_int, _vp, _c_int, _vp, _c_sz, _vp]),
     "impdar_fir_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
     "impdar_fir_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
+    "impdar_winavg_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int]),
+    "impdar_winavg_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _c_sz, _vp]),
+    "impdar_winavg_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _c_sz, _vp]),
+    "impdar_filtfilt_rows_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int, _c_int, _c_int]),
+    "impdar_filtfilt_rows_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _c_int, _vp, _c_int, _vp, _c_sz, _vp]),
+    "impdar_filtfilt_rows_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _c_int, _vp, _c_int, _vp, _c_sz, _vp]),
+    "impdar_rowabsmax_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "impdar_rowabsmax_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "impdar_rowgain_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _c_int, _vp]),
+    "impdar_rowgain_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _c_int, _vp]),
     "impdar_kirchhoff_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int]),
     "impdar_kirchhoff_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_dbl, _c_int, _c_int, _c_int,
                                       _vp, _c_sz, _vp]),
@@ -51,6 +61,9 @@ PROTOTYPES = {
     "impdar_stolt_debug_stop_after": (_c_int, [_c_int]),
     "impdar_phsh_set_legacy": (_c_int, [_c_int]),
     "impdar_phsh_workspace_bytes": (_c_sz, [_c_int, _c_int]),
+    "impdar_phsh_ffd_workspace_bytes": (_c_sz, [_c_int, _c_int]),
+    "impdar_phsh_ffd_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _vp, _vp, _c_dbl, _c_dbl,
+                                     _vp, _c_sz, _vp]),
     "impdar_phsh_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _vp, _vp, _c_dbl, _c_dbl,
                                  _vp, _c_sz, _vp]),
 }

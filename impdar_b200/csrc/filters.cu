@@ -3,6 +3,7 @@
 // All of these are HBM-bound: traces are the contiguous axis, so every kernel maps lanes to traces
 // (coalesced 128-bit accesses) and keeps per-row / per-trace state on chip.
 #include "common.cuh"
+#include "iir.cuh"
 
 namespace impdar {
 
@@ -379,23 +380,6 @@ __global__ void __launch_bounds__(256) ahfilt_strip_kernel(const T *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------ filtfilt
-struct IirCoef {
-    double b[33];
-    double a[33];
-    double zi[32];
-};
-
-// One step of the transposed direct-form II recurrence (scipy.signal.lfilter).  The feed-forward halves
-// t_i = b_{i+1} x + z_{i+1} do not depend on y, so the serial chain per sample is two DFMA (y, then z_0).
-template <typename T, int NS>
-__device__ __forceinline__ double iir_step(double xv, double (&z)[NS], const IirCoef &c) {
-    const double yv = fma(c.b[0], xv, z[0]);
-#pragma unroll
-    for (int i = 0; i < NS - 1; ++i) z[i] = fma(-c.a[i + 1], yv, fma(c.b[i + 1], xv, z[i + 1]));
-    z[NS - 1] = fma(-c.a[NS], yv, c.b[NS] * xv);
-    return yv;
-}
-
 // Software-pipelined recurrence over n strided samples: the next block of FF_U inputs is in flight while the current
 // block runs through the (serial, fp64-pipe bound) recurrence, so the HBM latency hides behind 21 DFMA per sample.
 constexpr int FF_U = 16;

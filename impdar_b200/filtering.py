@@ -196,6 +196,229 @@ def vertical_band_pass(self, low, high, order=5, filttype='butter', cheb_rp=5, f
     self.flags.bpass[2] = high
 
 
+# ------------------------------------------------------------------ sibling filters
+try:  # the reference's own exception class when ImpDAR is importable, so `except ImpdarError` keeps working
+    from impdar.lib.ImpdarError import ImpdarError
+except Exception:  # pragma: no cover - ImpDAR is not installed on the GPU box
+    class ImpdarError(Exception):
+        """Used for exceptions caused by something radar-y (ImpdarError.py:12)."""
+
+
+def filtfilt_rows_device(x, suffix, b, a):
+    """scipy.signal.filtfilt(b, a, x, axis=-1) (along the trace axis) on a (.., snum, tnum) CUDA tensor."""
+    import torch
+    lib = _lib.load()
+    S, T = x.shape[-2], x.shape[-1]
+    B = 1 if x.dim() == 2 else x.shape[0]
+    bb, aa, zi, padlen = iir_prepare(b, a)
+    if T <= padlen:
+        raise ValueError("The length of the input vector x must be greater than padlen, which is %d." % padlen)
+    out = torch.empty_like(x)
+    nbytes = lib.impdar_filtfilt_rows_workspace_bytes(S, T, B, padlen, x.element_size())
+    ws = device.workspace(nbytes)
+    fn = getattr(lib, 'impdar_filtfilt_rows_' + suffix)
+    _lib.check(fn(device.ptr(x), device.ptr(out), S, T, B, device.ptr(bb), device.ptr(aa), len(bb),
+                  device.ptr(zi), padlen, device.ptr(ws), ws.numel(), device.current_stream_ptr()))
+    return out
+
+
+def _horizontal_iir(self, b, a):
+    """``self.data = filtfilt(b, a, self.data)`` (_RadarDataFiltering.py:203, :273, :338): the result is float64
+    whatever the input dtype; a device-resident radargram stays on the device in its compute dtype."""
+    x, suffix, np_dtype, was_device = _stage(self.data)
+    out = filtfilt_rows_device(x, suffix, b, a)
+    _unstage(self, out, None if was_device else np.float64, was_device)
+    self.flags.hfilt = np.ones((2,))
+    self.flags.hfilt[1] = 3
+
+
+def _check_constant_spacing(self):
+    if self.flags.interp is None or not self.flags.interp[0]:
+        raise ImpdarError('This method can only be used on constantly spaced data')
+    if self.flags.elev:
+        raise ImpdarError('This will not work with elevation corrected data')
+
+
+def _horizontal_corner(self, wavelength, label):
+    """Shared arithmetic of highpass / lowpass (_RadarDataFiltering.py:170-199, :240-269)."""
+    tracespace = self.flags.interp[1]
+    wavelength = int(wavelength)
+    fsamp = 100.
+    nsamp = int(wavelength / tracespace)
+    if nsamp < 1:
+        raise ValueError('wavelength is too small, causing no samples per wavelength')
+    if nsamp > self.tnum:
+        raise ValueError('wavelength is too large, bigger than the whole radargram')
+    print('Sample resolution = {:d}'.format(nsamp))
+    high_corner_freq = fsamp / float(nsamp)
+    print('{:s} cutoff at {:4.2f} MHz...'.format(label, high_corner_freq))
+    nyquist_freq = (1. / self.dt) / 2.0
+    return high_corner_freq * 1.0e6 / nyquist_freq
+
+
+def highpass(self, wavelength):
+    """High pass in the horizontal for a given wavelength; mirrors _RadarDataFiltering.py:138-209."""
+    from scipy.signal import butter
+    _check_constant_spacing(self)
+    corner_freq = _horizontal_corner(self, wavelength, 'High')
+    b, a = butter(5, corner_freq, 'high')
+    _horizontal_iir(self, b, a)
+    print('Highpass filter complete.')
+
+
+def lowpass(self, wavelength):
+    """Low pass in the horizontal for a given wavelength; mirrors _RadarDataFiltering.py:212-279."""
+    from scipy.signal import butter
+    _check_constant_spacing(self)
+    corner_freq = _horizontal_corner(self, wavelength, 'Low')
+    b, a = butter(3, corner_freq, 'low')
+    _horizontal_iir(self, b, a)
+    print('Lowpass filter complete.')
+
+
+def horizontal_band_pass(self, low, high):
+    """Bandpass in the horizontal for a pair of wavelengths; mirrors _RadarDataFiltering.py:282-350."""
+    from scipy.signal import butter
+    _check_constant_spacing(self)
+    if low >= high:
+        raise ValueError('Low must be less than high')
+    if low <= 0.0:
+        raise ValueError('Low must be larger than 0 but is {:f}'.format(low))
+    tracespace = self.flags.interp[1]
+    fsamp = 100.
+    nsamp_high = int(low / tracespace)
+    nsamp_low = int(high / tracespace)
+    if nsamp_high < 1:
+        raise ValueError('Minimum wavelength is too small, causing no samples per wavelength')
+    if nsamp_low > self.tnum:
+        raise ValueError('Maximum wavelength is too long, causing more samples per wavelength than tnum, use lowpass instead?')
+    print('Sample resolution high = {:d}'.format(nsamp_high))
+    print('Sample resolution low = {:d}'.format(nsamp_low))
+    nyquist_freq = fsamp / 2.0
+    corner_freq = np.zeros((2,))
+    corner_freq[0] = (fsamp / float(nsamp_low)) / nyquist_freq
+    corner_freq[1] = (fsamp / float(nsamp_high)) / nyquist_freq
+    b, a = butter(5, corner_freq, 'bandpass')
+    _horizontal_iir(self, b, a)
+    print('Highpass filter complete.')
+
+
+def winavg_device(x, suffix, taper, half):
+    import torch
+    lib = _lib.load()
+    S, T = x.shape[-2], x.shape[-1]
+    B = 1 if x.dim() == 2 else x.shape[0]
+    out = torch.empty_like(x)
+    tp = device.to_device(taper, torch.float64)
+    nbytes = lib.impdar_winavg_workspace_bytes(S, T, B)
+    ws = device.workspace(nbytes) if nbytes else None
+    fn = getattr(lib, 'impdar_winavg_' + suffix)
+    _lib.check(fn(device.ptr(x), device.ptr(out), S, T, B, int(half), device.ptr(tp), device.ptr(ws),
+                  0 if ws is None else ws.numel(), device.current_stream_ptr()))
+    return out
+
+
+def winavg_hfilt(self, avg_win, taper='full', filtdepth=100):
+    """Moving-window average-trace removal; mirrors _RadarDataFiltering.py:353-440."""
+    if avg_win > self.tnum:
+        print('Cannot average over more than the whole data matrix. Reducing avg_win to tnum')
+        avg_win = self.tnum
+    if avg_win % 2 == 0:
+        avg_win = avg_win + 1
+        print('The averaging window must be an odd number of traces.')
+        print('The averaging window has been changed to {:d}'.format(avg_win))
+    exptaper = _exp_taper(self)
+    if taper == 'full':
+        pass
+    elif taper == 'pexp':
+        exptaper[:filtdepth] = exptaper[:filtdepth] - exptaper[filtdepth]
+        exptaper[filtdepth:self.snum] = 0
+        exptaper = exptaper / np.max(exptaper)
+    elif taper == 'tukey':
+        raise NotImplementedError("the hard-coded StoDeep 'tukey' taper is marked unused in the reference "
+                                  "(_RadarDataFiltering.py:410-415, pragma: no cover) and is not on the B200 path")
+    else:
+        raise ValueError('Unrecognized taper. Options are full, pexp, or tukey')
+    x, suffix, np_dtype, was_device = _stage(self.data)
+    out = winavg_device(x, suffix, exptaper, (int(avg_win) - 1) // 2)
+    _unstage(self, out, np_dtype, was_device)
+    self.flags.hfilt = np.zeros((2,))
+    self.flags.hfilt[1] = 2
+    print('Horizontal filter complete.')
+
+
+def rowgain_device(x, suffix, gain, trig=None, in_double=True):
+    """y[s, t] = x[s, t] * gain[s] for s > trig[t] (all rows when trig is None), in place."""
+    import torch
+    lib = _lib.load()
+    S, T = x.shape[-2], x.shape[-1]
+    B = 1 if x.dim() == 2 else x.shape[0]
+    g = device.to_device(np.ascontiguousarray(gain, dtype=np.float64), torch.float64)
+    tr = None if trig is None else torch.from_numpy(np.ascontiguousarray(trig, dtype=np.int32)).cuda()
+    fn = getattr(lib, 'impdar_rowgain_' + suffix)
+    _lib.check(fn(device.ptr(x), device.ptr(x), S, T, B, device.ptr(g), device.ptr(tr), int(bool(in_double)),
+                  device.current_stream_ptr()))
+    return x
+
+
+def _reject_integer_gain(np_dtype):
+    if np_dtype is not None and not np.issubdtype(np_dtype, np.floating):
+        # the reference multiplies in place by a float array, which numpy refuses for integer radargrams
+        raise TypeError("Cannot cast ufunc 'multiply' output from dtype('float64') to dtype('%s') "
+                        "with casting rule 'same_kind'" % np_dtype)
+
+
+def rangegain(self, slope):
+    """Linear range gain below the trigger sample; mirrors _RadarDataProcessing.py:456-471."""
+    x, suffix, np_dtype, was_device = _stage(self.data)
+    _reject_integer_gain(np_dtype)
+    tt = np.asarray(self.travel_time, dtype=np.float64).flatten()
+    gain = np.ones(self.snum)
+    if isinstance(self.trig, (float, int, np.int64)):
+        t0 = int(self.trig) + 1
+        # gain = travel_time[int(trig) + 1:] * slope, applied to data[int(trig + 1):, :]
+        start = int(self.trig + 1)
+        g = tt[t0:] * slope
+        if len(g) != max(self.snum - start, 0) and len(g) != 1:
+            raise ValueError('operands could not be broadcast together with shapes (%d,%d) (%d,1)'
+                             % (max(self.snum - start, 0), self.tnum, len(g)))
+        gain[start:] = g
+        out = rowgain_device(x, suffix, gain, None, True)
+    else:
+        trig = np.asarray(self.trig).astype(int).flatten()
+        # per-trace trigger: data[int(trig) + 1:, i] *= travel_time[int(trig) + 1:] * slope
+        out = rowgain_device(x, suffix, tt * slope, trig, True)
+    _unstage(self, out, np_dtype, was_device)
+    self.flags.rgain = True
+
+
+def rowabsmax_device(x, suffix):
+    import torch
+    lib = _lib.load()
+    S, T = x.shape[-2], x.shape[-1]
+    B = 1 if x.dim() == 2 else x.shape[0]
+    out = torch.empty((B, S) if x.dim() == 3 else (S,), dtype=torch.float64, device=x.device)
+    fn = getattr(lib, 'impdar_rowabsmax_' + suffix)
+    _lib.check(fn(device.ptr(x), device.ptr(out), S, T, B, device.current_stream_ptr()))
+    return out
+
+
+def agc(self, window=50, scaling_factor=50):
+    """Automatic gain control; mirrors _RadarDataProcessing.py:474-488.  The per-row max |data| is reduced on the
+    device; the (snum,) window maximum and the scale vector are O(snum * window) host work."""
+    x, suffix, np_dtype, was_device = _stage(self.data)
+    rowmax = device.to_host(rowabsmax_device(x, suffix), np.float64)
+    maxamp = np.zeros((self.snum,))
+    for i in range(self.snum):
+        maxamp[i] = np.max(rowmax[max(0, i - window // 2):min(i + window // 2, self.snum)])
+    maxamp[maxamp == 0] = 1.0e-6
+    dtype = np_dtype if np_dtype is not None else (np.float32 if suffix == 'f32' else np.float64)
+    scale = (scaling_factor / maxamp).astype(dtype).astype(np.float64)
+    out = rowgain_device(x, suffix, scale, None, False)
+    _unstage(self, out, np_dtype, was_device)
+    self.flags.agc = True
+
+
 def migrate(self, mtype='stolt', vtaper=10, htaper=10, tmig=0, vel_fn=None, vel=1.68e8, nxpad=10,
             nearfield=False, verbose=0):
     """Dispatch on mtype exactly like _RadarDataFiltering.py:590-637; the callables are looked up on

@@ -273,6 +273,28 @@ def phase_shift_device(data_dev, dt, dx, travel_time_us, vmig, htaper, vtaper, o
     return out
 
 
+def phase_shift_ffd_device(data_dev, dt, dx, dx_fd, travel_time_us, vmig, htaper, vtaper):
+    """Laterally varying v(x, z) branch (Fourier finite difference, mig_python.py:428-432, 466-481, 496-540):
+    (snum, tnum) float64 CUDA tensor + (snum, tnum) float64 vmig -> migrated (snum, tnum) float64."""
+    import torch
+    lib = _lib.load()
+    S, T = data_dev.shape
+    vm = np.ascontiguousarray(np.asarray(vmig, dtype=np.float64))
+    if vm.shape != (S, T):
+        raise ValueError('operands could not be broadcast together with shapes (%d,) %s' % (T, str(vm.shape[1:])))
+    out = torch.empty((S, T), dtype=torch.float64, device=data_dev.device)
+    ws = device.workspace(lib.impdar_phsh_ffd_workspace_bytes(S, T))
+    tt = device.host_f64(travel_time_us)
+    thr2 = ((tt / 1.0e6) / tt[-1] / 1e6) ** 2.                          # mig_python.py:484
+    vm_dev = device.to_device(vm, torch.float64)
+    th_dev = device.to_device(thr2, torch.float64)
+    rc = lib.impdar_phsh_ffd_f64(device.ptr(data_dev), device.ptr(out), S, T, float(dt), float(dx), float(dx_fd),
+                                 device.ptr(vm_dev), device.ptr(th_dev), float(htaper), float(vtaper),
+                                 device.ptr(ws), ws.numel(), device.current_stream_ptr())
+    _lib.check(rc)
+    return out
+
+
 def _reject_integer_inplace(dat):
     in_dtype = _np_dtype(dat.data)
     if in_dtype is not None and not np.issubdtype(in_dtype, np.floating):
@@ -302,12 +324,15 @@ def migrationPhaseShift(dat, vel=1.69e8, vel_fn=None, htaper=100, vtaper=1000, *
             raise ValueError('vmig needs to be an array or float')
         if len(vmig) != dat.snum:
             raise ValueError('Interpolated velocity profile is not the length of the number of samples in a trace.')
-        if hasattr(vmig[0], "__len__"):
-            raise NotImplementedError(
-                'impdar_b200: the laterally varying v(x,z) Fourier finite-difference branch '
-                '(mig_python.py:428-432, 466-481, 496-540) is not on the B200 path yet; there is no CPU fallback')
-    x = device.to_device(dat.data)
-    out = phase_shift_device(x, dat.dt, dx, dat.travel_time, vmig, htaper, vtaper)
+    if hasattr(vmig, "__len__") and hasattr(vmig[0], "__len__"):
+        import torch
+        print('2-D velocity structure, Fourier Finite-Difference Migration')
+        x = device.to_device(dat.data, torch.float64)
+        out = phase_shift_ffd_device(x, dat.dt, dx, float(np.mean(dat.trace_int)), dat.travel_time, vmig,
+                                     htaper, vtaper)
+    else:
+        x = device.to_device(dat.data)
+        out = phase_shift_device(x, dat.dt, dx, dat.travel_time, vmig, htaper, vtaper)
     _finish(dat, out, np.float64, was_device)
     print('Phase-Shift Migration of %.0fx%.0f matrix complete in %.2f seconds'
           % (dat.snum, dat.tnum, time.time() - start))

@@ -41,9 +41,16 @@ class RadarData(object):
         self.trace_int = trace_int
         self.flags = RadarFlags()
         self.fn = None
+        self.trig = 0
 
     adaptivehfilt = filtering.adaptivehfilt
     horizontalfilt = filtering.horizontalfilt
     hfilt = filtering.hfilt
     vertical_band_pass = filtering.vertical_band_pass
     migrate = filtering.migrate
+    highpass = filtering.highpass
+    lowpass = filtering.lowpass
+    horizontal_band_pass = filtering.horizontal_band_pass
+    winavg_hfilt = filtering.winavg_hfilt
+    rangegain = filtering.rangegain
+    agc = filtering.agc

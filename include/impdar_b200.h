@@ -6,11 +6,13 @@
  *   - migrationlib/mig_cython.h:11            void mig_kirch_loop(...)     the one C-ABI precedent
  *   - migrationlib/mig_python.py:35-123       migrationKirchhoff[Loop]
  *   - migrationlib/mig_python.py:126-208      migrationStolt
- *   - migrationlib/mig_python.py:211-287,361-493  migrationPhaseShift / phaseShift (const, layered)
+ *   - migrationlib/mig_python.py:211-287,361-540  migrationPhaseShift / phaseShift (const, layered, v(x,z) FFD)
  *   - migrationlib/mig_python.py:290-355      migrationTimeWavenumber (taper-only stub)
  *   - RadarData/_RadarDataFiltering.py:469-549  vertical_band_pass  (filtfilt / FIR lfilter)
  *   - RadarData/_RadarDataFiltering.py:93-135   horizontalfilt
  *   - RadarData/_RadarDataFiltering.py:19-90    adaptivehfilt
+ *   - RadarData/_RadarDataFiltering.py:138-440  highpass / lowpass / horizontal_band_pass / winavg_hfilt
+ *   - RadarData/_RadarDataProcessing.py:456-496 rangegain / agc
  *
  * Conventions
  *   - A radargram is a C-order (snum, tnum) array: row = time sample, column = trace, traces contiguous
@@ -92,6 +94,35 @@ int impdar_fir_f32(const float *x, float *y, int snum, int tnum, int batch, cons
 int impdar_fir_f64(const double *x, double *y, int snum, int tnum, int batch, const double *taps,
                    int ntaps, void *stream);
 
+/* ------------------------------------------------- sibling filters --- */
+/* winavg_hfilt (_RadarDataFiltering.py:353-440): y[s,i] = x[s,i] - (T)(mean(x[s, max(0,i-half) : min(T,i+half)])
+ * * taper[s]), half = (avg_win - 1) / 2 after the reference's odd/size corrections (:392-398); taper: device, snum
+ * doubles (the 'full' or 'pexp' taper, :399-409).  workspace: impdar_winavg_workspace_bytes() bytes (may be 0).  */
+size_t impdar_winavg_workspace_bytes(int snum, int tnum, int batch);
+int impdar_winavg_f32(const float *x, float *y, int snum, int tnum, int batch, int half, const double *taper,
+                      void *workspace, size_t workspace_bytes, void *stream);
+int impdar_winavg_f64(const double *x, double *y, int snum, int tnum, int batch, int half, const double *taper,
+                      void *workspace, size_t workspace_bytes, void *stream);
+/* highpass / lowpass / horizontal_band_pass (_RadarDataFiltering.py:138-350): scipy.signal.filtfilt(b, a, x, axis=-1),
+ * i.e. along the TRACE axis, one recurrence per sample row.  Arguments as impdar_filtfilt_*; tnum > padlen.        */
+size_t impdar_filtfilt_rows_workspace_bytes(int snum, int tnum, int batch, int padlen, int elem_bytes);
+int impdar_filtfilt_rows_f32(const float *x, float *y, int snum, int tnum, int batch, const double *b,
+                             const double *a, int ncoef, const double *zi, int padlen, void *workspace,
+                             size_t workspace_bytes, void *stream);
+int impdar_filtfilt_rows_f64(const double *x, double *y, int snum, int tnum, int batch, const double *b,
+                             const double *a, int ncoef, const double *zi, int padlen, void *workspace,
+                             size_t workspace_bytes, void *stream);
+/* agc / rangegain (_RadarDataProcessing.py:456-496).  rowabsmax: out[b*snum + s] = max_t |x[b,s,t]| (device doubles;
+ * NaN propagates).  rowgain: y[s,t] = x[s,t] * gain[s] where s > trig[t] (trig: device tnum ints, NULL = every
+ * row); gain: device snum doubles; in_double != 0 forms the product in float64 and casts back (numpy's in-place
+ * multiply by a float64 gain), 0 casts the gain to the data type first (agc's .astype(dtype)).  x == y allowed.   */
+int impdar_rowabsmax_f32(const float *x, double *out, int snum, int tnum, int batch, void *stream);
+int impdar_rowabsmax_f64(const double *x, double *out, int snum, int tnum, int batch, void *stream);
+int impdar_rowgain_f32(const float *x, float *y, int snum, int tnum, int batch, const double *gain, const int *trig,
+                       int in_double, void *stream);
+int impdar_rowgain_f64(const double *x, double *y, int snum, int tnum, int batch, const double *gain, const int *trig,
+                       int in_double, void *stream);
+
 /* ------------------------------------------------------ Kirchhoff (mig_python.py:35-123) --- */
 /* out[:, x - x_begin] for output traces x in [x_begin, x_end) of the (snum, tnum) radargram `data`
  * (the whole input is needed: the aperture is only limited by 2r/v <= max(tt)).
@@ -157,6 +188,17 @@ size_t impdar_phsh_workspace_bytes(int snum, int tnum);
 int impdar_phsh_f32(const float *data, float *out, int snum, int tnum, double dt, double dx, double vel,
                     const double *vmig, const double *thr2, double htaper, double vtaper,
                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* Laterally varying velocity v(x, z): split-step Fourier + explicit finite-difference branch of phaseShift
+ * (mig_python.py:428-432, 439-487; fourierFiniteDiff :496-525; Sp_Matr :528-540).  float64 end to end (the thin-lens
+ * phase reaches 1e9 rad and the update is one serial chain over snum * nt steps).
+ *   data, out : device (snum, tnum) doubles;  vmig : device (snum, tnum) doubles from getVelocityProfile (:606-640)
+ *   thr2 : device snum doubles (as above);  dx : mean trace spacing used for kx (:260-265);
+ *   dx_fd : np.mean(dat.trace_int), the spacing fourierFiniteDiff uses (:517)                            */
+size_t impdar_phsh_ffd_workspace_bytes(int snum, int tnum);
+int impdar_phsh_ffd_f64(const double *data, double *out, int snum, int tnum, double dt, double dx, double dx_fd,
+                        const double *vmig, const double *thr2, double htaper, double vtaper, void *workspace,
+                        size_t workspace_bytes, void *stream);
 
 /* Testing hook: 1 selects the one-frequency-bin-per-state kernels instead of the (+w, -w) pair kernels. */
 int impdar_phsh_set_legacy(int on);

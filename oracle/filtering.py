@@ -159,3 +159,113 @@ def filtfilt_explicit(b, a, x, padlen=None):
     y = run(ext)
     y = run(y[::-1])[::-1]
     return y[padlen:padlen + S]
+
+
+# --------------------------------------------------------------------------------------------
+# Sibling filters: winavg_hfilt, highpass / lowpass / horizontal_band_pass, rangegain, agc
+# --------------------------------------------------------------------------------------------
+
+
+def winavg_taper(travel_time_us, snum, taper='full', filtdepth=100):
+    """_RadarDataFiltering.py:399-417 (the hard-coded 'tukey' taper is marked unused there and is not restated)."""
+    exptaper = exp_taper(travel_time_us)
+    if taper == 'full':
+        pass
+    elif taper == 'pexp':
+        exptaper[:filtdepth] = exptaper[:filtdepth] - exptaper[filtdepth]
+        exptaper[filtdepth:snum] = 0
+        exptaper = exptaper / np.max(exptaper)
+    else:
+        raise ValueError('Unrecognized taper. Options are full, pexp, or tukey')
+    return exptaper
+
+
+def winavg_hfilt(data, travel_time_us, avg_win, taper='full', filtdepth=100):
+    """_RadarDataFiltering.py:353-440, the reference's own loop (it is O(T * avg_win * S), fine at test sizes)."""
+    data = np.asarray(data)
+    S, T = data.shape
+    if avg_win > T:
+        avg_win = T
+    if avg_win % 2 == 0:
+        avg_win = avg_win + 1
+    exptaper = winavg_taper(travel_time_us, S, taper, filtdepth)
+    out = np.zeros_like(data, dtype=data.dtype)
+    for i in range(int(T)):
+        range_start = max(i - ((avg_win - 1) // 2), 0)
+        range_end = min(i + ((avg_win - 1) // 2), T)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                avg_trace = np.mean(data[:, range_start:range_end], axis=-1) * exptaper
+        out[:, i] = data[:, i] - avg_trace
+    return out
+
+
+def horizontal_corner(wavelength, tracespace, dt, tnum):
+    """Corner frequency of highpass / lowpass, _RadarDataFiltering.py:176-199 / :246-269."""
+    wavelength = int(wavelength)
+    nsamp = int(wavelength / tracespace)
+    if nsamp < 1:
+        raise ValueError('wavelength is too small, causing no samples per wavelength')
+    if nsamp > tnum:
+        raise ValueError('wavelength is too large, bigger than the whole radargram')
+    return (100. / float(nsamp)) * 1.0e6 / ((1. / dt) / 2.0)
+
+
+def highpass(data, wavelength, tracespace, dt):
+    """_RadarDataFiltering.py:138-209: butter(5, 'high'), filtfilt along the last (trace) axis, float64 result."""
+    from scipy.signal import butter, filtfilt
+    b, a = butter(5, horizontal_corner(wavelength, tracespace, dt, data.shape[1]), 'high')
+    return filtfilt(b, a, data)
+
+
+def lowpass(data, wavelength, tracespace, dt):
+    """_RadarDataFiltering.py:212-279: butter(3, 'low')."""
+    from scipy.signal import butter, filtfilt
+    b, a = butter(3, horizontal_corner(wavelength, tracespace, dt, data.shape[1]), 'low')
+    return filtfilt(b, a, data)
+
+
+def horizontal_band_pass(data, low, high, tracespace):
+    """_RadarDataFiltering.py:282-350 (note: the Nyquist here is fsamp / 2 = 50, not 1 / (2 dt), :325)."""
+    from scipy.signal import butter, filtfilt
+    if low >= high:
+        raise ValueError('Low must be less than high')
+    if low <= 0.0:
+        raise ValueError('Low must be larger than 0 but is {:f}'.format(low))
+    nsamp_high = int(low / tracespace)
+    nsamp_low = int(high / tracespace)
+    if nsamp_high < 1:
+        raise ValueError('Minimum wavelength is too small, causing no samples per wavelength')
+    if nsamp_low > data.shape[1]:
+        raise ValueError('Maximum wavelength is too long, causing more samples per wavelength than tnum, use lowpass instead?')
+    corner = np.array([(100. / float(nsamp_low)) / 50., (100. / float(nsamp_high)) / 50.])
+    b, a = butter(5, corner, 'bandpass')
+    return filtfilt(b, a, data, axis=1)
+
+
+def rangegain(data, travel_time_us, trig, slope):
+    """_RadarDataProcessing.py:456-471."""
+    data = np.array(data, copy=True)
+    tt = np.asarray(travel_time_us)
+    if isinstance(trig, (float, int, np.int64)):
+        gain = tt[int(trig) + 1:] * slope
+        data[int(trig + 1):, :] *= np.atleast_2d(gain).transpose()
+    else:
+        for i, tr in enumerate(trig):
+            gain = tt[int(tr) + 1:] * slope
+            data[int(tr) + 1:, i] *= gain
+    return data
+
+
+def agc(data, window=50, scaling_factor=50):
+    """_RadarDataProcessing.py:474-488."""
+    data = np.array(data, copy=True)
+    S = data.shape[0]
+    maxamp = np.zeros((S,))
+    for i in range(S):
+        maxamp[i] = np.max(np.abs(data[max(0, i - window // 2):min(i + window // 2, S), :]))
+    maxamp[maxamp == 0] = 1.0e-6
+    data *= (scaling_factor / np.atleast_2d(maxamp).transpose()).astype(data.dtype)
+    return data

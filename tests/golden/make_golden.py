@@ -107,8 +107,68 @@ def run_filters(tag, data, **mk):
              order=kw.get("order", 5), **geom(d))
 
 
+def run_siblings(tag, data, **mk):
+    """winavg_hfilt, highpass / lowpass / horizontal_band_pass, rangegain, agc."""
+    S, T = data.shape
+    mk = dict(mk)
+    mk["tt0_us"] = mk.get("tt0_us", 0.0) + 0.001
+    for w, tp in ((1, 'full'), (7, 'full'), (10, 'pexp'), (T + 5, 'full')):
+        d = make_dat(data, **mk)
+        quiet(d.winavg_hfilt, w, taper=tp, filtdepth=S // 3)
+        save("%s_winavg_w%d_%s" % (tag, w, tp), data=data, out=d.data, avg_win=w, taper=tp, filtdepth=S // 3, **geom(d))
+    for name, args in (("highpass", (100.,)), ("lowpass", (60.,)), ("horizontal_band_pass", (40., 200.))):
+        d = make_dat(data, **mk)
+        d.flags.interp = np.array([1., 5.])
+        quiet(getattr(d, name), *args)
+        save("%s_%s" % (tag, name), data=data, out=d.data, args=np.array(args), tracespace=5., **geom(d))
+    d = make_dat(data, **mk)
+    d.trig = 3
+    quiet(d.rangegain, 1.0e-2)
+    save(tag + "_rangegain_scalar", data=data, out=d.data, trig=3, slope=1.0e-2, **geom(d))
+    d = make_dat(data, **mk)
+    d.trig = (np.arange(T) % 7).astype(float)
+    quiet(d.rangegain, 2.5e-2)
+    save(tag + "_rangegain_vector", data=data, out=d.data, trig=d.trig, slope=2.5e-2, **geom(d))
+    d = make_dat(data, **mk)
+    quiet(d.agc, window=20, scaling_factor=50)
+    save(tag + "_agc", data=data, out=d.data, window=20, scaling_factor=50, **geom(d))
+
+
+def run_lateral():
+    """Laterally varying velocity (Fourier finite-difference branch, mig_python.py:428-432, 466-481, 496-540) with the
+    reference's own test/input_data/velocity_lateral.txt table: even and odd shapes, plus the zeros fixture of
+    test_migrationlib.py:133-135."""
+    import warnings
+    warnings.simplefilter("ignore")
+    vel = np.genfromtxt(os.path.join(REF_ROOT, "test", "input_data", "velocity_lateral.txt"))
+    for tag, shape, seed in [("r32x48", (32, 48), 21), ("r33x50", (33, 50), 22), ("r64x40", (64, 40), 23)]:
+        rng = np.random.default_rng(seed)
+        data = rng.standard_normal(shape)
+        d = make_dat(data)
+        vmig = quiet(mig_python.getVelocityProfile, d, vel)
+        quiet(mig_python.migrationPhaseShift, d, vel=vel, htaper=5, vtaper=7)
+        assert np.isfinite(d.data).all()
+        save(tag + "_phsh_lateral", data=data, out=d.data, vel=vel, vmig=vmig, htaper=5, vtaper=7, **geom(d))
+    f = NoInit.NoInitRadarData(big=True)
+    x = f.data.copy()
+    quiet(mig_python.migrationPhaseShift, f, vel_fn=os.path.join(REF_ROOT, "test", "input_data", "velocity_lateral.txt"))
+    save("noinit_phsh_lateral", data=x, out=f.data, vel=vel, htaper=100, vtaper=1000, dt=f.dt,
+         travel_time=np.asarray(f.travel_time, dtype=np.float64), dist=np.asarray(f.dist, dtype=np.float64),
+         trace_int=np.asarray(f.trace_int, dtype=np.float64) * np.ones(f.tnum))
+
+
 def main():
     slow = "--slow" in sys.argv
+    if "--only-lateral" in sys.argv:
+        run_lateral()
+        return
+    if "--only-siblings" in sys.argv:
+        rng = np.random.default_rng(17)
+        run_siblings("r96x160", rng.standard_normal((96, 160)) + 2.0)
+        return
+    run_lateral()
+    rng = np.random.default_rng(17)
+    run_siblings("r96x160", rng.standard_normal((96, 160)) + 2.0)
     # (vi) seeded random shapes (SURVEY 8c)
     for tag, shape, seed, mk in [("r64x128", (64, 128), 11, {}),
                                  ("r65x50", (65, 50), 12, dict(tt0_us=0.013)),

@@ -223,3 +223,93 @@ def test_bad_mtype_and_ftype():
         d.hfilt(ftype='dummy')
     with pytest.raises(ValueError):
         d.vertical_band_pass(0.1, 100., filttype='dummy')
+
+
+# ------------------------------------------------------------------ sibling filters
+@pytest.mark.parametrize("name", golden_names(contains="_winavg_"))
+def test_winavg_golden(name):
+    g = load_golden(name)
+    d = dat_from_golden(g)
+    d.winavg_hfilt(int(g["avg_win"]), taper=str(g["taper"]), filtdepth=int(g["filtdepth"]))
+    assert d.flags.hfilt[0] == 0 and d.flags.hfilt[1] == 2
+    assert d.data.dtype == g["out"].dtype
+    assert _report(name, d.data, g["out"]) < 1e-13       # rel_l2 also checks the NaN pattern (avg_win = 1)
+    d32 = dat_from_golden(g, dtype=np.float32)
+    d32.winavg_hfilt(int(g["avg_win"]), taper=str(g["taper"]), filtdepth=int(g["filtdepth"]))
+    assert d32.data.dtype == np.float32
+    assert rel_l2(d32.data, g["out"]) < TOL
+    with pytest.raises(ValueError):
+        d.winavg_hfilt(5, taper='dummy')
+
+
+@pytest.mark.parametrize("name", ["r96x160_highpass", "r96x160_lowpass", "r96x160_horizontal_band_pass"])
+def test_horizontal_iir_golden(name):
+    from impdar_b200.filtering import ImpdarError
+    g = load_golden(name)
+    meth = name[len("r96x160_"):]
+    args = [float(a) for a in g["args"]]
+    d = dat_from_golden(g)
+    with pytest.raises(ImpdarError):            # not constantly spaced yet (flags.interp), :170 / :240 / :298
+        getattr(d, meth)(*args)
+    d.flags.interp = np.array([1., float(g["tracespace"])])
+    getattr(d, meth)(*args)
+    assert d.data.dtype == np.float64 and d.flags.hfilt[0] == 1 and d.flags.hfilt[1] == 3
+    assert _report(name, d.data, g["out"]) < 1e-6    # the recurrence itself differs ~1e-9 between fp64 orderings
+    d32 = dat_from_golden(g, dtype=np.float32)
+    d32.flags.interp = np.array([1., float(g["tracespace"])])
+    getattr(d32, meth)(*args)
+    assert d32.data.dtype == np.float64              # filtfilt returns float64 whatever the input (:203)
+    assert _report(name + "[f32]", d32.data, g["out"]) < TOL
+    d.flags.elev = 1
+    with pytest.raises(ImpdarError):
+        getattr(d, meth)(*args)
+
+
+@pytest.mark.parametrize("S,T", [(70, 1000), (33, 257), (200, 64)])
+def test_horizontal_iir_vs_oracle(S, T):
+    """Row counts that are not multiples of 32, trace counts that are not multiples of the 32-sample chunk."""
+    from oracle import filtering as of
+    d = synthetic_dat(S, T, seed=S + T, dtype=np.float64)
+    d.flags.interp = np.array([1., 5.])
+    want = of.highpass(d.data, 100., 5., d.dt)
+    d.highpass(100.)
+    assert _report("highpass %dx%d" % (S, T), d.data, want) < 1e-6
+    d = synthetic_dat(S, T, seed=S + T, dtype=np.float64)
+    d.flags.interp = np.array([1., 5.])
+    want = of.horizontal_band_pass(d.data, 40., 200., 5.) if T > 40 else None
+    if want is not None:
+        d.horizontal_band_pass(40., 200.)
+        assert _report("hbp %dx%d" % (S, T), d.data, want) < 1e-6
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_rangegain_") + golden_names(contains="_agc"))
+def test_gains_golden(name):
+    g = load_golden(name)
+    for dtype in (np.float64, np.float32):
+        d = dat_from_golden(g, dtype=dtype)
+        if "_agc" in name:
+            d.agc(window=int(g["window"]), scaling_factor=int(g["scaling_factor"]))
+            assert d.flags.agc is True
+        else:
+            d.trig = g["trig"] if g["trig"].ndim else int(g["trig"])
+            d.rangegain(float(g["slope"]))
+            assert d.flags.rgain is True
+        assert d.data.dtype == dtype
+        if dtype == np.float64:
+            assert np.array_equal(d.data, g["out"])          # one rounding per element: bit-exact
+        else:
+            assert _report(name + "[f32]", d.data, g["out"]) < TOL
+    d = dat_from_golden(g, dtype=np.int32)
+    with pytest.raises(TypeError):
+        d.trig = 0
+        d.rangegain(1.0)
+
+
+def test_winavg_long_rows_vs_oracle():
+    """Rows longer than the shared-memory prefix buffer take the global-scratch path."""
+    from oracle import filtering as of
+    d = synthetic_dat(16, 30000, seed=5, dtype=np.float64)
+    d.data += 10.0
+    want = of.winavg_hfilt(d.data[:, :], d.travel_time, 201)
+    d.winavg_hfilt(201)
+    assert _report("winavg 16x30000", d.data, want) < 1e-12

@@ -89,3 +89,35 @@ def test_loop_flavours_match():
     _, s2 = om.stolt_loops(x, 1e-8, np.ones(20) * 5., dist, 1.68e8, 3, 4)
     assert rel_l2(s1, s2) < 1e-12
     assert om.kirchhoff_pair_count(tt, dist, 1.69e8) > 0
+
+
+# ------------------------------------------------------------------ sibling filters
+@pytest.mark.parametrize("name", golden_names(contains="_winavg_"))
+def test_winavg(name):
+    g = load_golden(name)
+    out = of.winavg_hfilt(g["data"], g["travel_time"], int(g["avg_win"]), str(g["taper"]), int(g["filtdepth"]))
+    assert np.array_equal(np.isnan(out), np.isnan(g["out"]))
+    assert np.array_equal(np.nan_to_num(out), np.nan_to_num(g["out"]))
+
+
+@pytest.mark.parametrize("name", ["r96x160_highpass", "r96x160_lowpass", "r96x160_horizontal_band_pass"])
+def test_horizontal_iir(name):
+    g = load_golden(name)
+    if name.endswith("highpass"):
+        out = of.highpass(g["data"], float(g["args"][0]), float(g["tracespace"]), float(g["dt"]))
+    elif name.endswith("lowpass"):
+        out = of.lowpass(g["data"], float(g["args"][0]), float(g["tracespace"]), float(g["dt"]))
+    else:
+        out = of.horizontal_band_pass(g["data"], float(g["args"][0]), float(g["args"][1]), float(g["tracespace"]))
+    assert out.dtype == np.float64 and np.array_equal(out, g["out"])
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_rangegain_") + golden_names(contains="_agc"))
+def test_gains(name):
+    g = load_golden(name)
+    if "_agc" in name:
+        out = of.agc(g["data"], int(g["window"]), int(g["scaling_factor"]))
+    else:
+        trig = g["trig"] if g["trig"].ndim else int(g["trig"])
+        out = of.rangegain(g["data"], g["travel_time"], trig, float(g["slope"]))
+    assert np.array_equal(out, g["out"])
