@@ -17,6 +17,7 @@
 // All transforms are fp32 Stockham / four-step FFTs with radix-16/32 butterflies in registers (fft_regs.cuh)
 // and twiddle tables computed in fp64; the remap coordinate sqrt(j^2 + beta^2) is fp64 (one Newton step on
 // the fp32 square root).  tests/stolt_stage_model.py restates every stage in numpy with the same indexing.
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -525,12 +526,44 @@ FFTR_DI void remap_coord(int jj, float jjf, const RemapCol &rc, int &i0, float &
     w0 = sc - w1;
 }
 
+struct NoHook {
+    FFTR_DI void operator()() const {}
+};
+
+// 1-D TMA (cp.async.bulk) of one whole column into shared memory, completion counted on an mbarrier.
+FFTR_DI void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+FFTR_DI void bulk_load_column(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+    const unsigned sd = (unsigned)__cvta_generic_to_shared(smem_dst), sb = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the buffer are ordered before the copy
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sd), "l"(gsrc),
+                 "r"(bytes), "r"(sb)
+                 : "memory");
+}
+FFTR_DI void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned sb = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(sb),
+        "r"(parity)
+        : "memory");
+}
+
 // One Stockham step of radix R (Ls = 16 or 256) on the padded shared-memory sequence: item j reads x[j + t S/R],
 // multiplies by w_{Ls R}^{k t} (k = j mod Ls), transforms, and writes y[(j - k) R + k + t Ls] - to shared memory
 // again or, for the last inverse step, to the global column.
-template <int S, int R, int LS, int DIR, int NT, bool TO_GLOBAL>
+template <int S, int R, int LS, int DIR, int NT, bool TO_GLOBAL, class AfterLoad = NoHook>
 FFTR_DI void stockham_step(cf *__restrict__ buf, const cf *__restrict__ twS, const cf *__restrict__ tw2, int tid,
-                           cf *__restrict__ gdst) {
+                           cf *__restrict__ gdst, AfterLoad after_load = AfterLoad()) {
     constexpr int ITEMS = S / R / NT;
     constexpr int STR = S / R;  // multiple of 16
     static_assert(ITEMS >= 1 && STR % 16 == 0, "shape");
@@ -543,6 +576,7 @@ FFTR_DI void stockham_step(cf *__restrict__ buf, const cf *__restrict__ twS, con
         for (int t = 0; t < R; ++t) v[it][t] = src[t * (STR + STR / 16)];
     }
     if (!TO_GLOBAL) __syncthreads();
+    after_load();  // every element this thread needs is in registers
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
         const int j = tid + it * NT;
@@ -570,7 +604,11 @@ FFTR_DI void stockham_step(cf *__restrict__ buf, const cf *__restrict__ twS, con
 
 // S = 16 * 16 * R3.  NT = S/32 threads; thread tid owns the first-step items jA, jB (radix 16, elements j + t S/16) with
 // jB the frequency mirror of jA: element (jA, t) <-> (jB, 15 - t), so every remap coordinate serves two outputs.
-template <int S, int R3>
+//
+// PF (prefetch): the column is brought into the (then idle) transform buffer by one 1-D TMA bulk copy issued as soon as the
+// previous column's last step has its operands in registers, so the load overlaps that step's butterflies and global
+// stores instead of being waited for at the top of the loop; without PF the first step loads straight from global memory.
+template <int S, int R3, bool PF>
 __global__ void __launch_bounds__(S / 32, (S >= 8192 ? 2 : (S >= 4096 ? 4 : 8))) stolt_col_kernel(const __grid_constant__ ColParams p) {
     constexpr int NT = S / 32, NI = S / 16, NZ = S / 2;
     static_assert(16 * 16 * R3 == S && NT >= 32, "factorisation");
@@ -578,22 +616,38 @@ __global__ void __launch_bounds__(S / 32, (S >= 8192 ? 2 : (S >= 4096 ? 4 : 8)))
     cf *buf = reinterpret_cast<cf *>(smem_raw);
     cf *twS = buf + (S + S / 16);
     cf *tw2 = twS + 256;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(tw2 + 256);
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += NT) {
         twS[i] = p.twS[i];
         tw2[i] = p.tw2[i];
     }
     const int jA = (tid == 0) ? 0 : tid, jB = (tid == 0) ? NI / 2 : NI - tid;
+    unsigned phase = 0;
+    if (PF && tid == 0) {
+        mbar_init(bar, 1);
+        if ((int)blockIdx.x < p.ncols) bulk_load_column(buf, p.Dt + (size_t)blockIdx.x * S, S * (unsigned)sizeof(cf), bar);
+    }
+    if (PF) __syncthreads();  // the barrier is initialised before anyone waits on it
 
     for (int cb = blockIdx.x; cb < p.ncols; cb += gridDim.x) {
         const int c = cb % p.Th;  // column within its profile
         cf *col = p.Dt + (size_t)cb * S;
         cf vA[16], vB[16];
-        // ---- forward step 1 (radix 16, no twiddle) straight from global memory
+        // ---- forward step 1 (radix 16, no twiddle) from the prefetched copy, or straight from global memory
+        if (PF) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
 #pragma unroll
-        for (int t = 0; t < 16; ++t) vA[t] = __ldcs(col + jA + t * NI);
+            for (int t = 0; t < 16; ++t) vA[t] = buf[jA + t * NI];
 #pragma unroll
-        for (int t = 0; t < 16; ++t) vB[t] = __ldcs(col + jB + t * NI);
+            for (int t = 0; t < 16; ++t) vB[t] = buf[jB + t * NI];
+        } else {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) vA[t] = __ldcs(col + jA + t * NI);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) vB[t] = __ldcs(col + jB + t * NI);
+        }
         fft_reg<16, -1>(vA);
         fft_reg<16, -1>(vB);
         __syncthreads();  // the previous column's last shared-memory reads are done (also orders the table fill)
@@ -668,7 +722,15 @@ __global__ void __launch_bounds__(S / 32, (S >= 8192 ? 2 : (S >= 4096 ? 4 : 8)))
         for (int t = 0; t < 16; ++t) buf[17 * jB + t] = vB[t];
         __syncthreads();
         stockham_step<S, 16, 16, 1, NT, false>(buf, twS, tw2, tid, nullptr);
-        stockham_step<S, R3, 256, 1, NT, true>(buf, twS, tw2, tid, col);
+        if (PF) {
+            const int nxt = cb + gridDim.x;
+            stockham_step<S, R3, 256, 1, NT, true>(buf, twS, tw2, tid, col, [&]() {
+                __syncthreads();  // nobody reads the buffer any more: the next column may land in it
+                if (tid == 0 && nxt < p.ncols) bulk_load_column(buf, p.Dt + (size_t)nxt * S, S * (unsigned)sizeof(cf), bar);
+            });
+        } else {
+            stockham_step<S, R3, 256, 1, NT, true>(buf, twS, tw2, tid, col);
+        }
     }
 }
 
@@ -771,32 +833,46 @@ static int launch_rowB(const RowBParams &p, cudaStream_t st) {
     return IMPDAR_B200_OK;
 }
 
-template <int S, int R3>
+template <int S, int R3, bool PF>
 static int launch_col(const ColParams &p, cudaStream_t st) {
     constexpr int NT = S / 32;
-    const size_t smem = (size_t)(S + S / 16 + 512) * sizeof(cf);
+    const size_t smem = (size_t)(S + S / 16 + 512) * sizeof(cf) + 16;  // + the mbarrier
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
-        IMPDAR_CUDA(cudaFuncSetAttribute(stolt_col_kernel<S, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IMPDAR_CUDA(cudaFuncSetAttribute(stolt_col_kernel<S, R3, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int n = 0;
-        IMPDAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stolt_col_kernel<S, R3>, NT, smem));
+        IMPDAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stolt_col_kernel<S, R3, PF>, NT, smem));
         ctas_per_sm = n > 0 ? n : 1;
     }
     int grid = num_sms() * ctas_per_sm;
     if (grid > p.ncols) grid = p.ncols;
     ktimer_begin("stolt_col_kernel", st);
-    stolt_col_kernel<S, R3><<<grid, NT, smem, st>>>(p);
+    stolt_col_kernel<S, R3, PF><<<grid, NT, smem, st>>>(p);
     ktimer_end(st);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
 }
 
+// IMPDAR_STOLT_COL_PREFETCH=0 selects the variant without the TMA prefetch (development A/B switch).
+static bool col_prefetch() {
+    const char *e = getenv("IMPDAR_STOLT_COL_PREFETCH");
+    return !(e && e[0] == '0');
+}
+
 static int dispatch_col(int S, const ColParams &p, cudaStream_t st) {
+    if (!col_prefetch()) {
+        switch (S) {
+            case 1024: return launch_col<1024, 4, false>(p, st);
+            case 2048: return launch_col<2048, 8, false>(p, st);
+            case 4096: return launch_col<4096, 16, false>(p, st);
+            case 8192: return launch_col<8192, 32, false>(p, st);
+        }
+    }
     switch (S) {
-        case 1024: return launch_col<1024, 4>(p, st);
-        case 2048: return launch_col<2048, 8>(p, st);
-        case 4096: return launch_col<4096, 16>(p, st);
-        case 8192: return launch_col<8192, 32>(p, st);
+        case 1024: return launch_col<1024, 4, true>(p, st);
+        case 2048: return launch_col<2048, 8, true>(p, st);
+        case 4096: return launch_col<4096, 16, true>(p, st);
+        case 8192: return launch_col<8192, 32, true>(p, st);
     }
     set_error("stolt: unsupported column length %d", S);
     return IMPDAR_B200_EINVAL;
