@@ -15,31 +15,45 @@ def profiles_for_rank(n_profiles, rank, world):
     return list(range(rank, n_profiles, world))
 
 
-def kirchhoff_trace_cost(travel_time_us, dist_km, vel, n_depths=64):
-    """Relative work per output trace: number of in-aperture input traces summed over a subsample of depths."""
+def kirchhoff_trace_cost(travel_time_us, dist_km, vel, n_depths=32, n_traces=2048):
+    """Relative work per output trace: number of in-aperture input traces summed over a subsample of depths.
+
+    The count is a smooth (piecewise linear) function of the trace position, so for monotone trace positions it is
+    evaluated at `n_traces` evenly spaced traces and interpolated: O(n_depths * n_traces * log tnum) host work,
+    well under a millisecond, instead of a searchsorted over every trace per depth."""
     tt = np.asarray(travel_time_us, dtype=np.float64) / 1e6
     dist = np.asarray(dist_km, dtype=np.float64) * 1e3
+    T = len(dist)
     tmax = tt.max()
     zs = vel * tt / 2.0
     idx = np.unique(np.linspace(0, len(tt) - 1, min(n_depths, len(tt))).astype(int))
-    cost = np.zeros(len(dist))
-    monotone = np.all(np.diff(dist) >= 0)
-    for i in idx:
-        a2 = (vel * tmax / 2.0) ** 2 - zs[i] ** 2
-        if a2 < 0:
-            continue
-        if not monotone:
-            cost += len(dist)
-            continue
-        a = np.sqrt(a2)
-        cost += np.searchsorted(dist, dist + a, side='right') - np.searchsorted(dist, dist - a, side='left')
-    return cost + 1.0
+    a2 = (vel * tmax / 2.0) ** 2 - zs[idx] ** 2
+    a = np.sqrt(a2[a2 >= 0])
+    if T < 2 or not np.all(np.diff(dist) >= 0):
+        return np.full(T, float(len(a) * T) + 1.0)
+    pick = np.unique(np.linspace(0, T - 1, min(n_traces, T)).astype(int))
+    d = dist[pick]
+    hi = np.searchsorted(dist, (d[None, :] + a[:, None]).ravel(), side='right')
+    lo = np.searchsorted(dist, (d[None, :] - a[:, None]).ravel(), side='left')
+    cost = (hi - lo).reshape(len(a), len(pick)).sum(axis=0).astype(np.float64)
+    if len(pick) == T:
+        return cost + 1.0
+    return np.interp(np.arange(T), pick, cost) + 1.0
+
+
+_range_cache = {}
 
 
 def kirchhoff_output_ranges(tnum, world, travel_time_us, dist_km, vel, align=8):
     """[(x_begin, x_end)] per rank: contiguous, covering [0, tnum), balanced by pair count, boundaries
     aligned to the kernel's 8-trace CTA tile."""
-    cost = kirchhoff_trace_cost(travel_time_us, dist_km, vel)
+    tt = np.ascontiguousarray(travel_time_us, dtype=np.float64)
+    dk = np.ascontiguousarray(dist_km, dtype=np.float64)
+    key = (int(tnum), int(world), float(vel), int(align), hash(tt.tobytes()), hash(dk.tobytes()))
+    hit = _range_cache.get(key)
+    if hit is not None:
+        return list(hit)
+    cost = kirchhoff_trace_cost(tt, dk, vel)
     cum = np.concatenate([[0.0], np.cumsum(cost)])
     bounds = [0]
     for r in range(1, world):
@@ -48,7 +62,11 @@ def kirchhoff_output_ranges(tnum, world, travel_time_us, dist_km, vel, align=8):
         x = min(max(x, bounds[-1]), tnum)
         bounds.append(x)
     bounds.append(tnum)
-    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+    ranges = [(bounds[r], bounds[r + 1]) for r in range(world)]
+    if len(_range_cache) > 64:
+        _range_cache.clear()
+    _range_cache[key] = tuple(ranges)
+    return ranges
 
 
 def kirchhoff_output_range(tnum, rank, world, travel_time_us, dist_km, vel):
