@@ -6,7 +6,7 @@
 
 or, without ImpDAR installed, ``impdar_b200.RadarData`` offers the same hot-path methods.
 """
-from . import migrationlib, filtering, process  # noqa: F401  (process.process mirrors impdar.lib.process.process)
+from . import migrationlib, filtering, processing, process  # noqa: F401  (process.process mirrors impdar.lib.process.process)
 from .radardata import RadarData, RadarFlags  # noqa: F401
 from .migrationlib import (migrationKirchhoff, migrationStolt, migrationPhaseShift,  # noqa: F401
                            migrationTimeWavenumber, getVelocityProfile)
@@ -17,6 +17,9 @@ _MIGRATION_NAMES = ('migrationKirchhoff', 'migrationStolt', 'migrationPhaseShift
 _FILTER_NAMES = ('vertical_band_pass', 'horizontalfilt', 'adaptivehfilt',
                  # sibling filters on the same kernels
                  'highpass', 'lowpass', 'horizontal_band_pass', 'winavg_hfilt', 'rangegain', 'agc')
+# index / resampling operations either side of the path, bound from impdar_b200.processing
+_PROCESSING_NAMES = ('reverse', 'crop', 'hcrop', 'restack', 'nmo', 'constant_sample_depth_spacing',
+                     'traveltime_to_depth', 'constant_space', 'elev_correct')
 _saved = {}
 
 
@@ -35,6 +38,9 @@ def install():
     for name in _FILTER_NAMES:
         _saved[('rd', name)] = getattr(RefRadarData, name)
         setattr(RefRadarData, name, getattr(filtering, name))
+    for name in _PROCESSING_NAMES:
+        _saved[('rd', name)] = getattr(RefRadarData, name)
+        setattr(RefRadarData, name, getattr(processing, name))
 
 
 def uninstall():

@@ -66,6 +66,22 @@ PROTOTYPES = {
                                      _vp, _c_sz, _vp]),
     "impdar_phsh_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _vp, _vp, _c_dbl, _c_dbl,
                                  _vp, _c_sz, _vp]),
+    "impdar_interp_node_bytes": (_c_sz, []),
+    "impdar_crop_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "impdar_crop_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "impdar_crop_bytes": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "impdar_shift_traces_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
+    "impdar_shift_traces_f32_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
+    "impdar_shift_traces_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
+    "impdar_restack_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "impdar_restack_f32_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "impdar_restack_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "impdar_interp_rows_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
+    "impdar_interp_rows_f32_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
+    "impdar_interp_rows_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
+    "impdar_interp_cols_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
+    "impdar_interp_cols_f32_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
+    "impdar_interp_cols_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
 }
 
 _lib = None

@@ -9,10 +9,13 @@ same time: the upload of profile p+1, the kernels of profile p and the download 
 engines + SMs).  Under ``torchrun`` every rank takes the profiles ``p mod world == rank`` (no collective,
 SURVEY.md 8e).
 
-Same argument checks, same order of steps, same flags and same dtypes as the reference.  Steps that are not on the
-hot path (hcrop, restack, reverse, nmo, denoise, interp, crop) are delegated to the object's own methods - with
-``impdar_b200.install()`` on ImpDAR's RadarData these are the reference's - and split the device-resident chain
-where the reference orders them between filters and migration.  There is no CPU fallback for the hot-path steps.
+Same argument checks, same order of steps, same flags and same dtypes as the reference.  The index / resampling
+steps (hcrop, restack, reverse, nmo, crop - impdar_b200.processing) run on the device inside the
+same chain, so  hcrop -> restack -> reverse -> vbp -> hfilt -> ahfilt -> nmo -> crop -> migrate  is one upload and one
+download per profile.  Only denoise (scipy Wiener filter) and interp (GPS file I/O) stay host steps of the object's
+own methods and split the chain where the reference orders them (between nmo and crop).  One deviation: the reference
+applies hcrop while it is still checking arguments (process.py:111-119); here every argument is checked first, so a
+bad later argument leaves the profiles untouched.  There is no CPU fallback for the device steps.
 """
 import numpy as np
 
@@ -27,19 +30,34 @@ def _need(dat, name):
     return fn
 
 
-def _host_dtype_after(steps, in_dtype):
-    """dtype the reference leaves in dat.data after `steps` (filters keep it, Stolt follows np.fft.irfft2)."""
+def _host_dtype_after(steps, in_dtype, dat=None):
+    """dtype the reference leaves in dat.data after `steps`: filters, block crops and reverse keep it; restack
+    (np.zeros), nmo (np.empty) and the per-trace pretrigger crop allocate float64; Stolt follows np.fft.irfft2."""
     dt = np.dtype(in_dtype)
-    for name, _ in steps:
+    for name, args in steps:
         if name == 'migrate':
             dt = np.dtype(np.float32) if dt == np.float32 else np.dtype(np.float64)
+        elif name in ('restack', 'nmo'):
+            dt = np.dtype(np.float64)
+        elif name == 'crop' and args[2] == 'pretrig' and isinstance(getattr(dat, 'trig', None), np.ndarray):
+            dt = np.dtype(np.float64)
     return dt
 
 
 def _run_chain_on_device(dat, steps):
     """Apply (name, args) steps through the drop-in methods; dat.data is a CUDA tensor, so results stay on the GPU."""
     for name, args in steps:
-        if name == 'vbp':
+        if name == 'hcrop':
+            _need(dat, 'hcrop')(*args)
+        elif name == 'restack':
+            _need(dat, 'restack')(args)
+        elif name == 'rev':
+            _need(dat, 'reverse')()
+        elif name == 'nmo':
+            _need(dat, 'nmo')(*args)
+        elif name == 'crop':
+            _need(dat, 'crop')(*args)
+        elif name == 'vbp':
             dat.vertical_band_pass(*args)
         elif name == 'hfilt':
             dat.hfilt(ftype='hfilt', bounds=args)
@@ -90,10 +108,14 @@ def run_device_chain(dats, steps, n_streams=3):
             # integer radargrams need the reference's cast-back (truncation) after every step: per-step path
             _run_chain_on_device(dat, steps)
             continue
-        final_dtype = _host_dtype_after(steps, src.dtype)
+        final_dtype = _host_dtype_after(steps, src.dtype, dat)
         with torch.cuda.stream(streams[slot]):
             dat.data = device.to_device(src, torch.float32 if src.dtype == np.float32 else torch.float64)
-            _run_chain_on_device(dat, steps)
+            dat._b200_reference_dtypes = True       # restack / nmo produce the reference's float64 on the device
+            try:
+                _run_chain_on_device(dat, steps)
+            finally:
+                del dat._b200_reference_dtypes
             res = dat.data
             want = torch.float64 if final_dtype == np.float64 else torch.float32
             if res.dtype != want:
@@ -112,9 +134,7 @@ def process(RadarDataList, interp=None, rev=False, vbp=None, hfilt=None, ahfilt=
             hcrop=None, restack=None, denoise=None, migrate=None, n_streams=3, **kwargs):
     """Perform one or more processing steps on a list of RadarData; mirrors lib/process.py:72-197.
 
-    Returns True if a step was performed.  The hot-path steps (vbp, hfilt, ahfilt, migrate) run device resident."""
-    done_stuff = False
-
+    Returns True if a step was performed.  Every step except denoise / interp runs device resident."""
     # ---- argument checking, as the reference (process.py:101-134)
     if crop is not None:
         try:
@@ -130,9 +150,6 @@ def process(RadarDataList, interp=None, rev=False, vbp=None, hfilt=None, ahfilt=
             raise ValueError('First element of hcrop must be a float')
         except TypeError:
             raise TypeError('hcrop must be subscriptible')
-        for dat in RadarDataList:
-            _need(dat, 'hcrop')(*hcrop)
-        done_stuff = True
     if denoise is not None:
         try:
             assert (type(denoise[0]) is int)
@@ -150,64 +167,52 @@ def process(RadarDataList, interp=None, rev=False, vbp=None, hfilt=None, ahfilt=
         except (ValueError, TypeError, IndexError):
             raise ValueError('interp must be a target spacing (float) then a gps filename')
 
+    if restack is not None and isinstance(restack, (list, tuple)):
+        restack = int(restack[0])
+    if nmo is not None and isinstance(nmo, (float, int)):
+        print('One nmo value given. Assuming that this is the separation. \
+              Uice=1.6')
+        nmo = (nmo, 1.6)
+
+    # ---- the device-resident chain, in the reference's order (process.py:111-193)
+    head = []
+    if hcrop is not None:
+        head.append(('hcrop', hcrop))
     if restack is not None:
-        for dat in RadarDataList:
-            if isinstance(restack, (list, tuple)):
-                restack = int(restack[0])
-            _need(dat, 'restack')(restack)
-        done_stuff = True
-
+        head.append(('restack', restack))
     if rev:
-        for dat in RadarDataList:
-            _need(dat, 'reverse')()
-        done_stuff = True
-
-    # ---- the device-resident chain(s): filters, [host steps the reference orders in between], migration
-    filters = []
+        head.append(('rev', None))
     if vbp is not None:
-        filters.append(('vbp', tuple(vbp)))
+        head.append(('vbp', tuple(vbp)))
     if hfilt is not None:
-        filters.append(('hfilt', hfilt))
+        head.append(('hfilt', hfilt))
     if ahfilt:
-        filters.append(('ahfilt', ahfilt))
-    tail = [('migrate', None)] if migrate is not None else []
-    host_between = nmo is not None or denoise is not None or interp is not None or crop is not None
+        head.append(('ahfilt', ahfilt))
+    if nmo is not None:
+        head.append(('nmo', tuple(nmo)))
+    tail = []
+    if crop is not None:
+        tail.append(('crop', crop))
+    if migrate is not None:
+        tail.append(('migrate', None))
+    host_between = denoise is not None or interp is not None
 
     if not host_between:
-        run_device_chain(RadarDataList, filters + tail, n_streams)
-        done_stuff = done_stuff or bool(filters or tail)
-        return done_stuff
+        run_device_chain(RadarDataList, head + tail, n_streams)
+        return bool(head or tail)
 
-    run_device_chain(RadarDataList, filters, n_streams)
-    done_stuff = done_stuff or bool(filters)
-
-    if nmo is not None:
-        if isinstance(nmo, (float, int)):
-            print('One nmo value given. Assuming that this is the separation. \
-                  Uice=1.6')
-            nmo = (nmo, 1.6)
-        for dat in RadarDataList:
-            _need(dat, 'nmo')(*nmo)
-        done_stuff = True
+    run_device_chain(RadarDataList, head, n_streams)
 
     if denoise is not None:
         for dat in RadarDataList:
             _need(dat, 'denoise')(*denoise)
-        done_stuff = True
 
     if interp is not None:
         from impdar.lib.gpslib import interp as interpdeep   # the reference's own (process.py:24, :178)
         interpdeep(RadarDataList, float(interp[0]), interp[1])
-        done_stuff = True
-
-    if crop is not None:
-        for dat in RadarDataList:
-            _need(dat, 'crop')(*crop)
-        done_stuff = True
 
     run_device_chain(RadarDataList, tail, n_streams)
-    done_stuff = done_stuff or bool(tail)
-    return done_stuff
+    return True
 
 
 def process_sharded(RadarDataList, rank=None, world=None, **kwargs):

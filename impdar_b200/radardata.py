@@ -6,7 +6,7 @@ the same functions onto ImpDAR's own RadarData instead.
 """
 import numpy as np
 
-from . import filtering
+from . import filtering, processing
 
 
 class RadarFlags(object):
@@ -42,6 +42,13 @@ class RadarData(object):
         self.flags = RadarFlags()
         self.fn = None
         self.trig = 0
+        # trace-wise vectors and depth scale the index / resampling methods keep in step with the radargram
+        # (RadarData/__init__.py:132-204); None = absent
+        self.trace_num = None if data is None else np.arange(self.tnum) + 1
+        self.lat = self.long = self.x_coord = self.y_coord = self.elev = self.decday = self.pressure = None
+        self.nmo_depth = None
+        self.elevation = None
+        self.picks = None
 
     adaptivehfilt = filtering.adaptivehfilt
     horizontalfilt = filtering.horizontalfilt
@@ -54,3 +61,12 @@ class RadarData(object):
     winavg_hfilt = filtering.winavg_hfilt
     rangegain = filtering.rangegain
     agc = filtering.agc
+    reverse = processing.reverse
+    crop = processing.crop
+    hcrop = processing.hcrop
+    restack = processing.restack
+    nmo = processing.nmo
+    constant_sample_depth_spacing = processing.constant_sample_depth_spacing
+    traveltime_to_depth = processing.traveltime_to_depth
+    constant_space = processing.constant_space
+    elev_correct = processing.elev_correct

@@ -13,6 +13,7 @@
  *   - RadarData/_RadarDataFiltering.py:19-90    adaptivehfilt
  *   - RadarData/_RadarDataFiltering.py:138-440  highpass / lowpass / horizontal_band_pass / winavg_hfilt
  *   - RadarData/_RadarDataProcessing.py:456-496 rangegain / agc
+ *   - RadarData/_RadarDataProcessing.py:20-637  reverse / crop / hcrop / restack / nmo / constant_space / elev_correct
  *
  * Conventions
  *   - A radargram is a C-order (snum, tnum) array: row = time sample, column = trace, traces contiguous
@@ -202,6 +203,52 @@ int impdar_phsh_ffd_f64(const double *data, double *out, int snum, int tnum, dou
 
 /* Testing hook: 1 selects the one-frequency-bin-per-state kernels instead of the (+w, -w) pair kernels. */
 int impdar_phsh_set_legacy(int on);
+
+/* ------------------------------------ index / resampling operations (_RadarDataProcessing.py:20-637) --- */
+/* All bit-exact against the reference's numpy 2.3 / scipy 1.18 arithmetic (operation order, no FMA contraction).
+ * Suffix _f32 / _f64: input and output in that type (the device-resident lane); _f32_f64: float32 input,
+ * float64 output (what the reference produces on the host for a float32 radargram).
+ *
+ * crop (:238-313 crop, :352-421 hcrop, :20-29 reverse): y (r1-r0, c1-c0) = x[r0:r1, c0:c1], flip_lr != 0 = np.fliplr. */
+int impdar_crop_f32(const float *x, float *y, int snum, int tnum, int batch, int r0, int r1, int c0, int c1,
+                    int flip_lr, void *stream);
+int impdar_crop_f64(const double *x, double *y, int snum, int tnum, int batch, int r0, int r1, int c0, int c1,
+                    int flip_lr, void *stream);
+/* the same block copy for any element size in {1, 2, 4, 8, 16} bytes (integer and complex radargrams). */
+int impdar_crop_bytes(const void *x, void *y, int snum, int tnum, int batch, int r0, int r1, int c0, int c1,
+                      int flip_lr, int elem_bytes, void *stream);
+/* per-trace vertical shift with NaN fill (:314-330 crop(dimension='pretrig') with a trigger vector, shift = trig;
+ * :587-637 elev_correct, shift = -top_ind):  y[i, t] = x[i + shift[t], t] if 0 <= i + shift[t] < snum_in else NaN.
+ * shift: device, tnum ints.  y is (snum_out, tnum).                                                         */
+int impdar_shift_traces_f32(const float *x, float *y, int snum_in, int tnum, int snum_out, const int *shift,
+                            void *stream);
+int impdar_shift_traces_f32_f64(const float *x, double *y, int snum_in, int tnum, int snum_out, const int *shift,
+                                void *stream);
+int impdar_shift_traces_f64(const double *x, double *y, int snum_in, int tnum, int snum_out, const int *shift,
+                            void *stream);
+/* restack (:424-477): y (snum, tnum / traces) = np.mean over consecutive groups of `traces` columns, summed in
+ * numpy's pairwise order in the input precision.                                                            */
+int impdar_restack_f32(const float *x, float *y, int snum, int tnum, int traces, void *stream);
+int impdar_restack_f32_f64(const float *x, double *y, int snum, int tnum, int traces, void *stream);
+int impdar_restack_f64(const double *x, double *y, int snum, int tnum, int traces, void *stream);
+/* linear interpolation between two source rows (:66-188 nmo, :50-63 constant_sample_depth_spacing) or two source
+ * columns (:499-584 constant_space) per output row / column.  nodes: device array of snum_out (tnum_out) records
+ * of impdar_interp_node_bytes() bytes { int lo, hi; double a, b, den; int exact, pad; }, built on the host in
+ * float64 (O(n)).  mode 0 = scipy interp1d._call_linear: y = a*x[hi] + b*x[lo];  mode 1 = numpy.interp:
+ * slope = (x[hi]-x[lo])/den, y = slope*a + x[lo] (exact != 0: y = x[lo]; NaN: retried as slope*b + x[hi]).   */
+size_t impdar_interp_node_bytes(void);
+int impdar_interp_rows_f32(const float *x, float *y, int snum_in, int tnum, int snum_out, const void *nodes,
+                           int mode, void *stream);
+int impdar_interp_rows_f32_f64(const float *x, double *y, int snum_in, int tnum, int snum_out, const void *nodes,
+                               int mode, void *stream);
+int impdar_interp_rows_f64(const double *x, double *y, int snum_in, int tnum, int snum_out, const void *nodes,
+                           int mode, void *stream);
+int impdar_interp_cols_f32(const float *x, float *y, int snum, int tnum_in, int tnum_out, const void *nodes,
+                           int mode, void *stream);
+int impdar_interp_cols_f32_f64(const float *x, double *y, int snum, int tnum_in, int tnum_out, const void *nodes,
+                               int mode, void *stream);
+int impdar_interp_cols_f64(const double *x, double *y, int snum, int tnum_in, int tnum_out, const void *nodes,
+                           int mode, void *stream);
 
 #ifdef __cplusplus
 }

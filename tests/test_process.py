@@ -28,21 +28,38 @@ def test_argument_checks_like_reference():
         proc.process([_dat()], vbp=3)
     with pytest.raises(ValueError):
         proc.process([_dat()], interp=('x',))
-    with pytest.raises(NotImplementedError):                    # not a hot-path step and the stand-in has no restack
-        proc.process([_dat()], restack=3)
+    with pytest.raises(NotImplementedError):                    # denoise is a host step the stand-in does not carry
+        proc.process([_dat()], denoise=(1, 2))
 
 
 def test_step_order_and_chain_split(monkeypatch):
-    """Filters form one device chain with the migration unless the reference orders a host step in between."""
+    """Every device step forms one chain, in the reference's order (process.py:111-193), unless the reference
+    orders a host step (denoise, interp) in between."""
     calls = []
     monkeypatch.setattr(proc, 'run_device_chain', lambda dats, steps, n: calls.append([s[0] for s in steps]))
     d = _dat()
-    d.crop = lambda *a: calls.append('crop')
+    d.denoise = lambda *a: calls.append('denoise')
     assert proc.process([d], vbp=(2, 10), hfilt=(0, 40), ahfilt=10, migrate=True)
     assert calls == [['vbp', 'hfilt', 'ahfilt', 'migrate']]
     del calls[:]
-    assert proc.process([d], vbp=(2, 10), crop=(0.1, 'top', 'twtt'), migrate=True)
-    assert calls == [['vbp'], 'crop', ['migrate']]
+    assert proc.process([d], migrate=True, crop=(0.1, 'top', 'twtt'), nmo=10., ahfilt=10, vbp=(2, 10), rev=True,
+                        restack=(3,), hcrop=(5, 'left', 'tnum'))
+    assert calls == [['hcrop', 'restack', 'rev', 'vbp', 'ahfilt', 'nmo', 'crop', 'migrate']]
+    del calls[:]
+    assert proc.process([d], vbp=(2, 10), nmo=(10., 1.69e8), denoise=(3, 3), crop=(0.1, 'top', 'twtt'), migrate=True)
+    assert calls == [['vbp', 'nmo'], 'denoise', ['crop', 'migrate']]
+
+
+def test_chain_result_dtypes_follow_reference():
+    d = _dat()
+    f32, f64 = np.dtype(np.float32), np.dtype(np.float64)
+    assert proc._host_dtype_after([('vbp', (2, 10)), ('crop', (1., 'top', 'snum'))], f32, d) == f32
+    assert proc._host_dtype_after([('hcrop', (5., 'left', 'tnum')), ('migrate', None)], f32, d) == f32
+    assert proc._host_dtype_after([('restack', 3)], f32, d) == f64
+    assert proc._host_dtype_after([('nmo', (10., 1.69e8)), ('migrate', None)], f32, d) == f64
+    assert proc._host_dtype_after([('crop', (0., 'top', 'pretrig'))], f32, d) == f32     # scalar trigger: a view
+    d.trig = np.zeros(d.tnum)
+    assert proc._host_dtype_after([('crop', (0., 'top', 'pretrig'))], f32, d) == f64     # per-trace: NaN-padded f64
 
 
 def test_process_sharded_split():
@@ -84,6 +101,27 @@ def test_process_matches_stepwise_and_oracle():
     rel = np.linalg.norm(dats[0].data - want) / np.linalg.norm(want)
     print("process chain vs oracle rel-L2 %.3e" % rel)
     assert rel < 1e-5
+
+
+@pytest.mark.gpu
+def test_process_full_chain_matches_stepwise():
+    """hcrop -> restack -> reverse -> vbp -> hfilt -> nmo -> crop -> migrate in one device-resident chain equals the
+    same methods called one by one on host arrays (each of which is bit-exact / 1e-5 against the reference)."""
+    kw = dict(hcrop=(9, 'left', 'tnum'), restack=3, rev=True, vbp=(2, 10), hfilt=(0, 64), nmo=(30., 1.69e8),
+              crop=(0.3, 'top', 'twtt'), migrate=True)
+    for dtype in (np.float32, np.float64):
+        d = synthetic_dat(300, 520, seed=3, dtype=dtype)
+        r = synthetic_dat(300, 520, seed=3, dtype=dtype)
+        for o in (d, r):
+            o.trig = np.zeros(o.tnum)
+        assert impdar_b200.process.process([d], **kw)
+        r.hcrop(*kw['hcrop']); r.restack(3); r.reverse(); r.vertical_band_pass(2, 10)
+        r.hfilt(ftype='hfilt', bounds=(0, 64)); r.nmo(*kw['nmo']); r.crop(*kw['crop']); r.migrate(mtype='stolt')
+        assert isinstance(d.data, np.ndarray) and d.data.dtype == r.data.dtype == np.float64
+        assert d.data.shape == r.data.shape and d.snum == r.snum and d.tnum == r.tnum
+        assert np.array_equal(d.travel_time, r.travel_time) and np.array_equal(d.dist, r.dist)
+        assert np.allclose(d.data, r.data, rtol=0, atol=2e-6 * np.abs(r.data).max())
+        assert d.flags.mig == 'stolt' and d.flags.restack and d.flags.reverse and d.flags.crop[0] == 1
 
 
 @pytest.mark.gpu
