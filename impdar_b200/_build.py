@@ -40,20 +40,27 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library.  Returns the library path."""
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile every .cu under csrc/ into one shared library.  Returns the library path.
+    `defines` / `out` build a variant (kernel A/B experiments) next to the default library."""
+    if out is not None:
+        return _build_variant(list(defines), out, verbose)
     if not force and not needs_build():
         return LIB
+    return _build_variant([], LIB, verbose)
+
+
+def _build_variant(defines, LIB, verbose):
     nvcc = find_nvcc()
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
     objs = []
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", "_".join(d.replace("=", "-") for d in defines) or "default")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + ["-I", INCLUDE, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
@@ -73,4 +80,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -7,7 +7,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libimpdar_b200.so")
+# IMPDAR_B200_LIB selects another build of the same library (development A/B runs of kernel variants)
+LIB_PATH = os.environ.get("IMPDAR_B200_LIB") or os.path.join(HERE, "libimpdar_b200.so")
 
 _c_int = ctypes.c_int
 _c_dbl = ctypes.c_double
@@ -46,6 +47,9 @@ PROTOTYPES = {
     "impdar_kirchhoff_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int]),
     "impdar_kirchhoff_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_dbl, _c_int, _c_int, _c_int,
                                       _vp, _c_sz, _vp]),
+    "impdar_kirchhoff_host_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int]),
+    "impdar_kirchhoff_host_pipelined_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_dbl, _c_int, _c_int,
+                                                     _vp, _c_sz, _vp]),
     "impdar_kirchhoff_enable_stats": (_c_int, [_c_int]),
     "impdar_kirchhoff_last_stats": (_c_int, [_vp, _vp]),
     "impdar_kirchhoff_set_mode": (_c_int, [_c_int]),

@@ -2,6 +2,8 @@
 // Reference semantics: RadarData/_RadarDataFiltering.py (line numbers in include/impdar_b200.h).
 // All of these are HBM-bound: traces are the contiguous axis, so every kernel maps lanes to traces
 // (coalesced 128-bit accesses) and keeps per-row / per-trace state on chip.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "iir.cuh"
 
@@ -382,11 +384,14 @@ __global__ void __launch_bounds__(256) ahfilt_strip_kernel(const T *__restrict__
 // ------------------------------------------------------------------------------------------ filtfilt
 // Software-pipelined recurrence over n strided samples: the next block of FF_U inputs is in flight while the current
 // block runs through the (serial, fp64-pipe bound) recurrence, so the HBM latency hides behind 21 DFMA per sample.
-constexpr int FF_U = 16;
+#ifndef IMPDAR_FF_U
+#define IMPDAR_FF_U 16
+#endif
+constexpr int FF_U = IMPDAR_FF_U;
 
 // `src` walks n samples with stride `ss` elements (negative = backwards), each mapped through `pre` (the odd
 // extension 2 x_edge - x of the pads, or the identity); results go to `dst` with stride `ds` when STORE.
-template <typename T, typename BUF, int NS, bool STORE, typename Pre>
+template <typename T, typename BUF, int NS, bool STORE, bool BZ, typename Pre>
 __device__ __forceinline__ void iir_run(int n, double (&z)[NS], const IirCoef &c, const T *__restrict__ src,
                                         long long ss, T *__restrict__ dst, long long ds, Pre pre) {
     BUF cur[FF_U], nxt[FF_U];
@@ -401,7 +406,7 @@ __device__ __forceinline__ void iir_run(int n, double (&z)[NS], const IirCoef &c
             src += FF_U * ss;
 #pragma unroll
             for (int u = 0; u < FF_U; ++u) {
-                const double yv = iir_step<T, NS>((double)cur[u], z, c);
+                const double yv = iir_step<T, NS, BZ>((double)cur[u], z, c);
                 if (STORE) dst[u * ds] = (T)yv;
             }
             if (STORE) dst += FF_U * ds;
@@ -410,14 +415,14 @@ __device__ __forceinline__ void iir_run(int n, double (&z)[NS], const IirCoef &c
         }
 #pragma unroll
         for (int u = 0; u < FF_U; ++u) {
-            const double yv = iir_step<T, NS>((double)cur[u], z, c);
+            const double yv = iir_step<T, NS, BZ>((double)cur[u], z, c);
             if (STORE) dst[u * ds] = (T)yv;
         }
         if (STORE) dst += FF_U * ds;
         i += FF_U;
     }
     for (; i < n; ++i) {
-        const double yv = iir_step<T, NS>((double)pre(*src), z, c);
+        const double yv = iir_step<T, NS, BZ>((double)pre(*src), z, c);
         src += ss;
         if (STORE) {
             *dst = (T)yv;
@@ -426,8 +431,8 @@ __device__ __forceinline__ void iir_run(int n, double (&z)[NS], const IirCoef &c
     }
 }
 
-template <typename T, int NS>
-__global__ void __launch_bounds__(64) filtfilt_kernel(const T *__restrict__ x, T *__restrict__ y,
+template <typename T, int NS, bool BZ>
+__global__ void __launch_bounds__(256) filtfilt_kernel(const T *__restrict__ x, T *__restrict__ y,
                                                       T *__restrict__ work, int S, int Tn, long long ntraces,
                                                       int padlen, const __grid_constant__ IirCoef c) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -449,10 +454,10 @@ __global__ void __launch_bounds__(64) filtfilt_kernel(const T *__restrict__ x, T
 #pragma unroll
         for (int i = 0; i < NS; ++i) z[i] = c.zi[i] * e0;
     }
-    iir_run<T, double, NS, true>(padlen, z, c, xb + (long long)padlen * st, -st, wk, st,
+    iir_run<T, double, NS, true, BZ>(padlen, z, c, xb + (long long)padlen * st, -st, wk, st,
                                  [&](T v) { return 2.0 * x0 - (double)v; });
-    iir_run<T, T, NS, true>(S, z, c, xb, st, wk + (long long)padlen * st, st, [](T v) { return v; });
-    iir_run<T, double, NS, true>(padlen, z, c, xb + (long long)(S - 2) * st, -st, wk + (long long)(padlen + S) * st, st,
+    iir_run<T, T, NS, true, BZ>(S, z, c, xb, st, wk + (long long)padlen * st, st, [](T v) { return v; });
+    iir_run<T, double, NS, true, BZ>(padlen, z, c, xb + (long long)(S - 2) * st, -st, wk + (long long)(padlen + S) * st, st,
                                  [&](T v) { return 2.0 * xl - (double)v; });
     // ---- backward over the forward output
     {
@@ -460,20 +465,22 @@ __global__ void __launch_bounds__(64) filtfilt_kernel(const T *__restrict__ x, T
 #pragma unroll
         for (int i = 0; i < NS; ++i) z[i] = c.zi[i] * e0;
     }
-    iir_run<T, T, NS, false>(padlen, z, c, wk + (long long)(L - 1) * st, -st, (T *)nullptr, 0, [](T v) { return v; });
-    iir_run<T, T, NS, true>(S, z, c, wk + (long long)(padlen + S - 1) * st, -st, yb + (long long)(S - 1) * st, -st,
+    iir_run<T, T, NS, false, BZ>(padlen, z, c, wk + (long long)(L - 1) * st, -st, (T *)nullptr, 0, [](T v) { return v; });
+    iir_run<T, T, NS, true, BZ>(S, z, c, wk + (long long)(padlen + S - 1) * st, -st, yb + (long long)(S - 1) * st, -st,
                             [](T v) { return v; });
 }
 
 template <typename T, int NS>
 static int launch_filtfilt(const T *x, T *y, T *work, int S, int Tn, int batch, int padlen, const IirCoef &c,
-                           cudaStream_t st) {
+                           bool odd_b_zero, cudaStream_t st) {
     const long long ntraces = (long long)batch * Tn;
     // one trace per thread: small problems use one warp per CTA so that every SM gets work
-    const int block = (ntraces < (long long)num_sms() * 64 * 2) ? 32 : 64;
+    int block = (ntraces < (long long)num_sms() * 64 * 2) ? 32 : 64;
+    if (const char *e = getenv("IMPDAR_FF_BLOCK")) block = atoi(e);   // development A/B switch
     const long long grid = (ntraces + block - 1) / block;
     ktimer_begin("filtfilt_kernel", st);
-    filtfilt_kernel<T, NS><<<(unsigned)grid, block, 0, st>>>(x, y, work, S, Tn, ntraces, padlen, c);
+    if (odd_b_zero) filtfilt_kernel<T, NS, true><<<(unsigned)grid, block, 0, st>>>(x, y, work, S, Tn, ntraces, padlen, c);
+    else filtfilt_kernel<T, NS, false><<<(unsigned)grid, block, 0, st>>>(x, y, work, S, Tn, ntraces, padlen, c);
     ktimer_end(st);
     IMPDAR_LAUNCH_CHECK();
     return IMPDAR_B200_OK;
@@ -500,8 +507,10 @@ static int filtfilt_impl(const T *x, T *y, int S, int Tn, int batch, const doubl
     cudaStream_t st = (cudaStream_t)stream;
     const int ns = ncoef - 1;
     T *work = (T *)ws;
+    bool odd_b_zero = ncoef >= 3;        // band-pass numerators: skip the DFMAs that multiply an exact zero
+    for (int i = 1; i < ncoef; i += 2) odd_b_zero = odd_b_zero && (b[i] == 0.0);
 #define FF_CASE(N) \
-    if (ns <= N) return launch_filtfilt<T, N>(x, y, work, S, Tn, batch, padlen, c, st);
+    if (ns <= N) return launch_filtfilt<T, N>(x, y, work, S, Tn, batch, padlen, c, odd_b_zero, st);
     FF_CASE(2) FF_CASE(4) FF_CASE(6) FF_CASE(8) FF_CASE(10) FF_CASE(12) FF_CASE(16) FF_CASE(24) FF_CASE(32)
 #undef FF_CASE
     set_error("filtfilt: unsupported order");

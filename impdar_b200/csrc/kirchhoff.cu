@@ -365,6 +365,7 @@ struct KirchTabParams {
     const int *flags;
     unsigned long long *stats;
     int S, T, Tp, Apad, A1, ldo, x_begin, x_end;
+    int s_begin, s_end;  // output rows of this launch (the host pipeline runs the image in row chunks)
 };
 
 __global__ void __launch_bounds__(128) kirch_table_build_kernel(int2 *__restrict__ tab, float *__restrict__ tabn,
@@ -410,8 +411,9 @@ __global__ void __launch_bounds__(128) kirch_table_build_kernel(int2 *__restrict
 // d/dt (np.gradient stencil) into the padded row-major layout; also the non-finite scan.
 __global__ void __launch_bounds__(256) grad_padded_kernel(const float *__restrict__ data, float *__restrict__ gP,
                                                           float *__restrict__ dP, int S, int T, int Tp, int Apad,
-                                                          const double *__restrict__ coef, int *__restrict__ flags) {
-    const int s = blockIdx.y;
+                                                          const double *__restrict__ coef, int *__restrict__ flags,
+                                                          int s0) {
+    const int s = s0 + blockIdx.y;
     const double a = coef[s], b = coef[S + s], c = coef[2 * S + s];
     bool bad = false;
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < T; x += gridDim.x * blockDim.x) {
@@ -493,7 +495,7 @@ __device__ __forceinline__ void kirch_table_loop(const KirchTabParams &p, int ti
 
 template <bool NEAR, bool STATS>
 __global__ void __launch_bounds__(128) kirch_table_kernel(const __grid_constant__ KirchTabParams p) {
-    const int ti = blockIdx.x;
+    const int ti = p.s_begin + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int xbase = p.x_begin + (blockIdx.y * 4 + warp) * (32 * KT_R) + lane;
     if (xbase - lane >= p.x_end) return;
@@ -534,7 +536,7 @@ __global__ void __launch_bounds__(256) kirch_table_fixup_kernel(const __grid_con
         const int e = amb_list[it / nblk];
         const int ti = e / tp.A1, m = e % tp.A1;
         const int xi = tp.x_begin + (int)(it % nblk) * 32 + lane;
-        if (xi >= tp.x_end) continue;
+        if (xi >= tp.x_end || ti < tp.s_begin || ti >= tp.s_end) continue;
         const double dxi = gp.dist[xi];
         float term = 0.f;
         if (xi - m >= 0) term += exact_term<NEAR>(gp, ti, xi - m, dxi);
@@ -545,6 +547,43 @@ __global__ void __launch_bounds__(256) kirch_table_fixup_kernel(const __grid_con
 }
 
 static inline int kirch_sp(int S) { return ((S + 64 + 31) / 32) * 32; }
+
+// float32 rows -> float64 rows (the reference returns float64, mig_python.py:95/:118); runs on the download stream
+__global__ void __launch_bounds__(256) widen_f32_f64_kernel(const float *__restrict__ x, double *__restrict__ y, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = (double)x[i];
+}
+
+// Host-to-host pipeline state (impdar_kirchhoff_host_pipelined_f64): an output row ti only reads input rows >= ti - 1
+// (the diffraction hyperbola runs downwards in time), so the image is processed bottom-up in row chunks:
+// upload chunk j-1 | d/dt + diffraction sum of chunk j | widen + download chunk j+1 on three streams.
+constexpr int KP_MAX_CHUNKS = 32;
+struct KirchPipe {
+    const float *h_in;   // host (pinned for a truly asynchronous copy), (S, T)
+    double *h_out;       // host, (S, T)
+    float *d_in;         // device (S, T)
+    double *d_stage;     // device (S, T)
+    int nchunks;
+    cudaStream_t up, down;
+    cudaEvent_t ev_up[KP_MAX_CHUNKS], ev_done[KP_MAX_CHUNKS], ev_entry, ev_exit;
+};
+static KirchPipe g_pipe;
+static int g_pipe_dev = -1;
+static int kirch_pipe_streams() {
+    int dev = 0;
+    IMPDAR_CUDA(cudaGetDevice(&dev));
+    if (g_pipe_dev == dev) return IMPDAR_B200_OK;
+    IMPDAR_CUDA(cudaStreamCreateWithFlags(&g_pipe.up, cudaStreamNonBlocking));
+    IMPDAR_CUDA(cudaStreamCreateWithFlags(&g_pipe.down, cudaStreamNonBlocking));
+    for (int i = 0; i < KP_MAX_CHUNKS; ++i) {
+        IMPDAR_CUDA(cudaEventCreateWithFlags(&g_pipe.ev_up[i], cudaEventDisableTiming));
+        IMPDAR_CUDA(cudaEventCreateWithFlags(&g_pipe.ev_done[i], cudaEventDisableTiming));
+    }
+    IMPDAR_CUDA(cudaEventCreateWithFlags(&g_pipe.ev_entry, cudaEventDisableTiming));
+    IMPDAR_CUDA(cudaEventCreateWithFlags(&g_pipe.ev_exit, cudaEventDisableTiming));
+    g_pipe_dev = dev;
+    return IMPDAR_B200_OK;
+}
 
 static unsigned long long *g_last_stats = nullptr;
 static cudaStream_t g_last_stats_stream = nullptr;
@@ -574,9 +613,9 @@ size_t impdar_kirchhoff_workspace_bytes(int S, int T, int nearfield) {
     return b + 4096;
 }
 
-int impdar_kirchhoff_f32(const float *data, float *out, int S, int T, const double *dist_m, const double *tt_s,
-                         const double *grad_coef, double vel, int nearfield, int x_begin, int x_end,
-                         void *workspace, size_t ws_bytes, void *stream) {
+static int kirchhoff_impl(const float *data, float *out, int S, int T, const double *dist_m, const double *tt_s,
+                          const double *grad_coef, double vel, int nearfield, int x_begin, int x_end,
+                          void *workspace, size_t ws_bytes, void *stream, const KirchPipe *pipe) {
     IMPDAR_CHECK_ARG(data && out && dist_m && tt_s && grad_coef, "kirchhoff: null pointer");
     IMPDAR_CHECK_ARG(S >= 2 && T >= 1, "kirchhoff: need snum >= 2, tnum >= 1");
     IMPDAR_CHECK_ARG(0 <= x_begin && x_begin < x_end && x_end <= T, "kirchhoff: bad output range [%d, %d)",
@@ -697,31 +736,64 @@ int impdar_kirchhoff_f32(const float *data, float *out, int S, int T, const doub
                                                           1.0 / dt_eff, eps_t, amb_list, amb_count);
             IMPDAR_LAUNCH_CHECK();
         }
-        {
-            int gx = (T + 255) / 256;
-            if (gx > 64) gx = 64;
-            dim3 grid(gx, S);
-            grad_padded_kernel<<<grid, 256, 0, st>>>(data, gP, dP, S, T, Tp, Apad, d_coef, flags);
-            IMPDAR_LAUNCH_CHECK();
-        }
         KirchTabParams tp;
         tp.gP = gP; tp.dP = dP; tp.tab = tab; tp.tabn = tabn; tp.nm = nm; tp.out = out; tp.flags = flags;
         tp.stats = stats; tp.S = S; tp.T = T; tp.Tp = Tp; tp.Apad = Apad; tp.A1 = A1; tp.ldo = x_end - x_begin;
         tp.x_begin = x_begin; tp.x_end = x_end;
-        dim3 grid(S, (x_end - x_begin + 4 * 32 * KT_R - 1) / (4 * 32 * KT_R));
-        if (g_stats_enabled) {
-            if (nearfield) { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<true, true><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
-            else { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<false, true><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
-        } else {
-            if (nearfield) { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<true, false><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
-            else { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<false, false><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
-        }
-        IMPDAR_LAUNCH_CHECK();
-        // exact pass over flagged table entries (reads the same padded row-major images)
         p.gradT = gP; p.dataT = dP; p.rowmajor = 1; p.Tp = Tp; p.Apad = Apad;
-        if (nearfield) kirch_table_fixup_kernel<true><<<num_sms() * 2, 256, 0, st>>>(tp, p, amb_list, amb_count);
-        else kirch_table_fixup_kernel<false><<<num_sms() * 2, 256, 0, st>>>(tp, p, amb_list, amb_count);
-        IMPDAR_LAUNCH_CHECK();
+        // Row chunks, bottom-up.  Without a host pipeline this is one chunk covering the whole image.
+        const int nchunks = pipe ? pipe->nchunks : 1;
+        int g_hi = S;   // d/dt rows [g_hi, S) are built
+        int u_hi = S;   // input rows [u_hi, S) are uploaded
+        for (int j = nchunks - 1; j >= 0; --j) {
+            const int r0 = (int)((long long)S * j / nchunks), r1 = (int)((long long)S * (j + 1) / nchunks);
+            if (r1 <= r0) continue;
+            if (pipe) {
+                // rows r0 - 1 .. : what the d/dt stencil of rows >= r0 reads
+                const int u0 = r0 > 0 ? r0 - 1 : 0;
+                if (u0 < u_hi) {
+                    IMPDAR_CUDA(cudaMemcpyAsync(pipe->d_in + (size_t)u0 * T, pipe->h_in + (size_t)u0 * T,
+                                                (size_t)(u_hi - u0) * T * sizeof(float), cudaMemcpyHostToDevice, pipe->up));
+                    u_hi = u0;
+                }
+                IMPDAR_CUDA(cudaEventRecord(pipe->ev_up[j], pipe->up));
+                IMPDAR_CUDA(cudaStreamWaitEvent(st, pipe->ev_up[j], 0));
+            }
+            {
+                const int g0 = r0;   // row r0 - 1 is uploaded (or r0 == 0: one-sided stencil)
+                int gx = (T + 255) / 256;
+                if (gx > 64) gx = 64;
+                dim3 grid(gx, g_hi - g0);
+                grad_padded_kernel<<<grid, 256, 0, st>>>(data, gP, dP, S, T, Tp, Apad, d_coef, flags, g0);
+                IMPDAR_LAUNCH_CHECK();
+                g_hi = g0;
+            }
+            tp.s_begin = r0; tp.s_end = r1;
+            dim3 grid(r1 - r0, (x_end - x_begin + 4 * 32 * KT_R - 1) / (4 * 32 * KT_R));
+            if (g_stats_enabled) {
+                if (nearfield) { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<true, true><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
+                else { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<false, true><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
+            } else {
+                if (nearfield) { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<true, false><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
+                else { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<false, false><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
+            }
+            IMPDAR_LAUNCH_CHECK();
+            // exact pass over flagged table entries of these rows (reads the same padded row-major images)
+            if (nearfield) kirch_table_fixup_kernel<true><<<num_sms() * 2, 256, 0, st>>>(tp, p, amb_list, amb_count);
+            else kirch_table_fixup_kernel<false><<<num_sms() * 2, 256, 0, st>>>(tp, p, amb_list, amb_count);
+            IMPDAR_LAUNCH_CHECK();
+            if (pipe) {
+                IMPDAR_CUDA(cudaEventRecord(pipe->ev_done[j], st));
+                IMPDAR_CUDA(cudaStreamWaitEvent(pipe->down, pipe->ev_done[j], 0));
+                const size_t n = (size_t)(r1 - r0) * T, off = (size_t)r0 * T;
+                int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+                if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+                widen_f32_f64_kernel<<<blocks, 256, 0, pipe->down>>>(out + off, pipe->d_stage + off, n);
+                IMPDAR_LAUNCH_CHECK();
+                IMPDAR_CUDA(cudaMemcpyAsync(pipe->h_out + off, pipe->d_stage + off, n * sizeof(double), cudaMemcpyDeviceToHost,
+                                            pipe->down));
+            }
+        }
     } else {
         IMPDAR_CHECK_ARG((unsigned long long)(T + 32) * (unsigned long long)kirch_sp(S) < (1ull << 32),
                          "kirchhoff: (tnum + 32) * padded snum must stay below 2^32 elements");
@@ -735,6 +807,8 @@ int impdar_kirchhoff_f32(const float *data, float *out, int S, int T, const doub
             w += tbytes;
         }
         IMPDAR_CUDA(cudaMemsetAsync(gradT, 0, tbytes * (nearfield ? 2 : 1), st));
+        if (pipe)  // irregular geometry: no row pipeline, the whole input goes up first
+            IMPDAR_CUDA(cudaMemcpyAsync(pipe->d_in, pipe->h_in, (size_t)S * T * sizeof(float), cudaMemcpyHostToDevice, st));
         {
             dim3 grid((T + 31) / 32, (S + 31) / 32), block(32, 8);
             grad_transpose_kernel<<<grid, block, 0, st>>>(data, gradT, dataT, S, T, SP, d_coef, flags);
@@ -750,11 +824,66 @@ int impdar_kirchhoff_f32(const float *data, float *out, int S, int T, const doub
             else { ktimer_begin("kirch_general_kernel", st); kirch_general_kernel<false, false><<<grid, block, 0, st>>>(p); ktimer_end(st); }
         }
         IMPDAR_LAUNCH_CHECK();
+        if (pipe) {
+            const size_t n = (size_t)S * T;
+            widen_f32_f64_kernel<<<num_sms() * 8, 256, 0, st>>>(out, pipe->d_stage, n);
+            IMPDAR_LAUNCH_CHECK();
+            IMPDAR_CUDA(cudaMemcpyAsync(pipe->h_out, pipe->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
     }
     g_last_stats = stats;
     g_last_stats_stream = st;
     g_last_path = use_table ? 2 : 1;
     return IMPDAR_B200_OK;
+}
+
+int impdar_kirchhoff_f32(const float *data, float *out, int S, int T, const double *dist_m, const double *tt_s,
+                         const double *grad_coef, double vel, int nearfield, int x_begin, int x_end,
+                         void *workspace, size_t ws_bytes, void *stream) {
+    return kirchhoff_impl(data, out, S, T, dist_m, tt_s, grad_coef, vel, nearfield, x_begin, x_end, workspace, ws_bytes,
+                          stream, nullptr);
+}
+
+size_t impdar_kirchhoff_host_workspace_bytes(int S, int T, int nearfield) {
+    const size_t n = (size_t)S * (size_t)T;
+    return impdar_kirchhoff_workspace_bytes(S, T, nearfield) + n * (2 * sizeof(float) + sizeof(double)) + 1024;
+}
+
+int impdar_kirchhoff_host_pipelined_f64(const float *h_data, double *h_out, int S, int T, const double *dist_m,
+                                        const double *tt_s, const double *grad_coef, double vel, int nearfield,
+                                        int nchunks, void *workspace, size_t ws_bytes, void *stream) {
+    IMPDAR_CHECK_ARG(h_data && h_out, "kirchhoff_host_pipelined: null pointer");
+    IMPDAR_CHECK_ARG(S >= 2 && T >= 1, "kirchhoff: need snum >= 2, tnum >= 1");
+    IMPDAR_CHECK_ARG(nchunks >= 1 && nchunks <= KP_MAX_CHUNKS, "kirchhoff_host_pipelined: nchunks must be in [1, %d]", KP_MAX_CHUNKS);
+    const size_t need = impdar_kirchhoff_host_workspace_bytes(S, T, nearfield);
+    IMPDAR_CHECK_ARG(workspace && ws_bytes >= need, "kirchhoff_host_pipelined: workspace too small (%zu < %zu)", ws_bytes, need);
+    int rc = kirch_pipe_streams();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)S * (size_t)T;
+    char *w = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    KirchPipe pipe = g_pipe;
+    pipe.h_in = h_data;
+    pipe.h_out = h_out;
+    pipe.d_stage = (double *)w;
+    w += n * sizeof(double);
+    pipe.d_in = (float *)w;
+    w += n * sizeof(float);
+    float *d_out = (float *)w;
+    w += n * sizeof(float);
+    pipe.nchunks = nchunks;
+    // the side streams start after whatever the caller's stream has queued on this workspace ...
+    IMPDAR_CUDA(cudaEventRecord(pipe.ev_entry, st));
+    IMPDAR_CUDA(cudaStreamWaitEvent(pipe.up, pipe.ev_entry, 0));
+    IMPDAR_CUDA(cudaStreamWaitEvent(pipe.down, pipe.ev_entry, 0));
+    rc = kirchhoff_impl(pipe.d_in, d_out, S, T, dist_m, tt_s, grad_coef, vel, nearfield, 0, T, w,
+                        ws_bytes - (size_t)(w - (char *)workspace), stream, &pipe);
+    // ... and the caller's stream finishes after them: one synchronisation on `stream` covers the downloads
+    cudaEventRecord(pipe.ev_exit, pipe.down);
+    cudaStreamWaitEvent(st, pipe.ev_exit, 0);
+    cudaEventRecord(pipe.ev_exit, pipe.up);
+    cudaStreamWaitEvent(st, pipe.ev_exit, 0);
+    return rc;
 }
 
 int impdar_kirchhoff_set_mode(int mode) {

@@ -608,8 +608,14 @@ FFTR_DI void stockham_step(cf *__restrict__ buf, const cf *__restrict__ twS, con
 // PF (prefetch): the column is brought into the (then idle) transform buffer by one 1-D TMA bulk copy issued as soon as the
 // previous column's last step has its operands in registers, so the load overlaps that step's butterflies and global
 // stores instead of being waited for at the top of the loop; without PF the first step loads straight from global memory.
+#ifndef COL_MINB_8192
+#define COL_MINB_8192 2
+#define COL_MINB_4096 4
+#define COL_MINB_SMALL 8
+#endif
+#define COL_MINB(S) ((S) >= 8192 ? COL_MINB_8192 : ((S) >= 4096 ? COL_MINB_4096 : COL_MINB_SMALL))
 template <int S, int R3, bool PF>
-__global__ void __launch_bounds__(S / 32, (S >= 8192 ? 2 : (S >= 4096 ? 4 : 8))) stolt_col_kernel(const __grid_constant__ ColParams p) {
+__global__ void __launch_bounds__(S / 32, COL_MINB(S)) stolt_col_kernel(const __grid_constant__ ColParams p) {
     constexpr int NT = S / 32, NI = S / 16, NZ = S / 2;
     static_assert(16 * 16 * R3 == S && NT >= 32, "factorisation");
     extern __shared__ __align__(16) unsigned char smem_raw[];

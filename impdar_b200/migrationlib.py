@@ -98,15 +98,42 @@ def kirchhoff_device(data_dev, travel_time_us, dist_km, vel, nearfield, x_begin=
     return out
 
 
+def kirchhoff_host(data, travel_time_us, dist_km, vel, nearfield, nchunks=None):
+    """Host numpy radargram -> host float64 migrated image with upload, kernels and download overlapped in row
+    chunks (impdar_kirchhoff_host_pipelined_f64).  The result lives in page-locked memory owned by the array."""
+    import torch
+    device.require_cuda()
+    lib = _lib.load()
+    a = np.asarray(data)
+    if a.dtype != np.float32 or not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a, dtype=np.float32)         # the device path computes in float32
+    S, T = a.shape
+    tt_sec = device.host_f64(travel_time_us) / 1.0e6
+    dist_m = np.ascontiguousarray(device.host_f64(dist_km) * 1.0e3)
+    if not np.all(np.diff(tt_sec) > 0):
+        raise ValueError('travel_time must be strictly ascending for Kirchhoff migration')
+    coef = gradient_coefficients(tt_sec)
+    if nchunks is None:
+        nchunks = 8 if S * T >= (1 << 20) and S >= 64 else 1
+    host_out = torch.empty((S, T), dtype=torch.float64, pin_memory=True)
+    ws = device.workspace(lib.impdar_kirchhoff_host_workspace_bytes(S, T, int(bool(nearfield))))
+    rc = lib.impdar_kirchhoff_host_pipelined_f64(device.ptr(a), device.ptr(host_out), S, T, device.ptr(dist_m),
+                                                 device.ptr(tt_sec), device.ptr(coef), float(vel), int(bool(nearfield)),
+                                                 int(nchunks), device.ptr(ws), ws.numel(), device.current_stream_ptr())
+    torch.cuda.current_stream().synchronize()                 # `a` and the vectors stay alive until here
+    _lib.check(rc)
+    return host_out.numpy()
+
+
 def migrationKirchhoff(dat, vel=1.69e8, nearfield=False):
     """Kirchhoff diffraction summation; mirrors mig_python.py:63-123 (dat.data becomes float64)."""
     print('Kirchhoff Migration (diffraction summation) of %.0fx%.0f matrix' % (dat.snum, dat.tnum))
     _check_data_shape(dat)
     start = time.time()
-    was_device = device.is_device_array(dat.data)
-    x = device.to_device(dat.data)
-    out = kirchhoff_device(x, dat.travel_time, dat.dist, vel, nearfield)
-    _finish(dat, out, np.float64, was_device)
+    if device.is_device_array(dat.data):
+        dat.data = kirchhoff_device(device.to_device(dat.data), dat.travel_time, dat.dist, vel, nearfield)
+    else:
+        dat.data = kirchhoff_host(dat.data, dat.travel_time, dat.dist, vel, nearfield)
     print('Kirchhoff Migration of %.0fx%.0f matrix complete in %.2f seconds'
           % (dat.snum, dat.tnum, time.time() - start))
     return dat

@@ -138,6 +138,16 @@ size_t impdar_kirchhoff_workspace_bytes(int snum, int tnum, int nearfield);
 int impdar_kirchhoff_f32(const float *data, float *out, int snum, int tnum, const double *dist_m,
                          const double *tt_s, const double *grad_coef, double vel, int nearfield,
                          int x_begin, int x_end, void *workspace, size_t workspace_bytes, void *stream);
+/* Host-to-host Kirchhoff with the transfers overlapped (the RadarData.migrate(mtype='kirch') call on a host array):
+ * h_data HOST (snum, tnum) floats, h_out HOST (snum, tnum) doubles - page-locked memory makes the copies truly
+ * asynchronous.  An output row only reads input rows at or below it (the hyperbola runs downwards in time), so the
+ * image is processed bottom-up in `nchunks` row chunks: upload | d/dt + diffraction sum | widen to float64 + download
+ * on three streams.  Uniform trace spacing only; irregular geometry runs the three phases back to back.  The call
+ * returns after enqueueing; synchronise `stream` before reading h_out.                                           */
+size_t impdar_kirchhoff_host_workspace_bytes(int snum, int tnum, int nearfield);
+int impdar_kirchhoff_host_pipelined_f64(const float *h_data, double *h_out, int snum, int tnum, const double *dist_m,
+                                        const double *tt_s, const double *grad_coef, double vel, int nearfield,
+                                        int nchunks, void *workspace, size_t workspace_bytes, void *stream);
 /* Counters of the last impdar_kirchhoff_f32 call (for the roofline): (output sample, input trace) pairs
  * inside the aperture and pairs that took the float64 exact path.  Counting pairs costs an instruction
  * per pair, so it is off unless enabled.  last_stats synchronises the stream of that call.            */
