@@ -172,6 +172,8 @@ class Workload(object):
 class KirchhoffC2(Workload):
     """configs[1]: Kirchhoff, 4096 traces x 2048 samples, v = 1.69e8; one independent radargram per GPU."""
     name = "kirchhoff_4096tr_x_2048smp_v1.69e8"
+    e2e_api = ("impdar_b200.RadarData.migrate(mtype='kirch') on host numpy data (pinned input): "
+               "impdar_kirchhoff_host_pipelined_f64, 8 row chunks, upload | kernels | float64 download overlapped")
     S, T = 2048, 4096
     nearfield = False
 

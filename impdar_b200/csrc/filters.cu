@@ -388,6 +388,17 @@ __global__ void __launch_bounds__(256) ahfilt_strip_kernel(const T *__restrict__
 #define IMPDAR_FF_U 16
 #endif
 constexpr int FF_U = IMPDAR_FF_U;
+// Optional L2 prefetch distance in blocks of FF_U rows (prefetch.global.L2 of the rows FF_PD blocks ahead).  Measured on
+// B200 (profiles/r01g_filtfilt_prefetch_ab.txt): 0.529 ms without, 0.567 / 0.568 / 0.604 ms with FF_PD = 2 / 4 / 8 for
+// 8 x 2048 x 8192 - the extra requests cost more than the L2 hits save, so it is off.
+#ifndef IMPDAR_FF_PD
+#define IMPDAR_FF_PD 0
+#endif
+constexpr int FF_PD = IMPDAR_FF_PD;
+template <typename T>
+__device__ __forceinline__ void prefetch_l2(const T *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 // `src` walks n samples with stride `ss` elements (negative = backwards), each mapped through `pre` (the odd
 // extension 2 x_edge - x of the pads, or the identity); results go to `dst` with stride `ds` when STORE.
@@ -403,6 +414,10 @@ __device__ __forceinline__ void iir_run(int n, double (&z)[NS], const IirCoef &c
         for (; i + 2 * FF_U <= n; i += FF_U) {
 #pragma unroll
             for (int u = 0; u < FF_U; ++u) nxt[u] = pre(src[u * ss]);
+            if (FF_PD > 0 && i + (2 + FF_PD) * FF_U <= n) {
+#pragma unroll
+                for (int u = 0; u < FF_U; ++u) prefetch_l2(src + (long long)(FF_PD * FF_U + u) * ss);
+            }
             src += FF_U * ss;
 #pragma unroll
             for (int u = 0; u < FF_U; ++u) {

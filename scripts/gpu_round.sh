@@ -21,7 +21,7 @@ if has bench; then
   echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -2 | tee $O/bench_reference_$TAG.json
 fi
 if has quick; then
-  echo "== quick"; timeout 600 python scripts/quick_gpu.py kirch stolt filters phsh kmodes 2>&1 | tee $O/quick_$TAG.log
+  echo "== quick"; timeout 600 python scripts/quick_gpu.py kirch stolt filters phsh kmodes indexops 2>&1 | tee $O/quick_$TAG.log
 fi
 if has launches; then
   for wl in $WLS; do

@@ -69,3 +69,16 @@ if 'kmodes' in which:
             ms=ev(lambda: ml.kirchhoff_device(x,tt,dist,1.69e8,True))
             print(f'kirch[{name}] near {S}x{T}: {ms:.2f} ms',flush=True)
         ml.set_kirchhoff_mode(0)
+
+if 'indexops' in which:
+    from impdar_b200 import processing as pr
+    S,T=4096,16384
+    x=torch.randn(S,T,device='cuda'); n=S*T
+    ms=ev(lambda: pr.crop_device(x,100,S,50,T)); print(f'crop {S}x{T}: {ms:.3f} ms {(S-100)*(T-50)*8/ms*1e3/1e9:.0f} GB/s',flush=True)
+    ms=ev(lambda: pr.crop_device(x,0,S,0,T,True)); print(f'reverse: {ms:.3f} ms {n*8/ms*1e3/1e9:.0f} GB/s',flush=True)
+    ms=ev(lambda: pr.restack_device(x,'f32',torch.float32,5)); print(f'restack 5: {ms:.3f} ms {n*4.8/ms*1e3/1e9:.0f} GB/s (4 B read + 0.8 B write per sample)',flush=True)
+    tt=np.arange(S)*0.01; nmot=np.sqrt((tt+0.3)**2-0.09); new=np.arange(0,nmot.max(),0.01)
+    nodes=pr.linear_nodes_scipy(nmot,new[new>=nmot[0]])
+    ms=ev(lambda: pr.interp_rows_device(x,'f32',torch.float32,nodes,0)); print(f'nmo rows ({len(nodes)} out rows): {ms:.3f} ms {len(nodes)*T*8/ms*1e3/1e9:.0f} GB/s (L2 serves the second source row)',flush=True)
+    sh=np.random.default_rng(0).integers(0,40,T)
+    ms=ev(lambda: pr.shift_traces_device(x,'f32',torch.float32,sh,S)); print(f'shift traces: {ms:.3f} ms {n*8/ms*1e3/1e9:.0f} GB/s',flush=True)
