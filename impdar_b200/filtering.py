@@ -419,6 +419,42 @@ def agc(self, window=50, scaling_factor=50):
     self.flags.agc = True
 
 
+def wiener_device(x, suffix, vert_win, hor_win, noise=None):
+    """scipy.signal.wiener on a (snum, tnum) CUDA tensor -> (float64 result, scratch tensor [sum of lVar, zero flag])."""
+    import torch
+    lib = _lib.load()
+    S, T = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty((S, T), dtype=torch.float64, device=x.device)
+    scratch = torch.zeros(2, dtype=torch.float64, device=x.device)
+    fn = getattr(lib, 'impdar_wiener_' + suffix)
+    _lib.check(fn(device.ptr(x), device.ptr(out), S, T, int(vert_win), int(hor_win), int(noise is None),
+                  0.0 if noise is None else float(noise), device.ptr(scratch), device.current_stream_ptr()))
+    return out, scratch
+
+
+def denoise(self, vert_win=1, hor_win=10, noise=None, ftype='wiener'):
+    """Denoising filter; mirrors _RadarDataFiltering.py:552-587.  The Wiener filter runs on the device in float64
+    (result float64 like scipy's); with noise=None a local variance of exactly zero raises the reference's ValueError."""
+    if ftype == 'wiener':
+        import torch
+        x, suffix, np_dtype, was_device = _stage(self.data)
+        out, scratch = wiener_device(x, suffix, vert_win, hor_win, noise)
+        if noise is None:
+            flag = int(scratch.view(torch.int32)[2].item())           # the int at byte 8
+            total = float(scratch[0].item())
+            if (flag & 1) and total != 0.0:                           # noise / 0 with noise != 0: numpy's 'divide' error
+                raise ValueError('Could not compute variance, specify noise for denoise')
+        if was_device:
+            self.data = out if x.dtype == torch.float64 else out.float()
+        else:
+            self.data = device.to_host(out, np.float64)
+    elif ftype == 'median':
+        raise NotImplementedError('the median denoising filter (scipy.ndimage.median_filter) is outside the B200 hot '
+                                  'path - use the reference for ftype=median')
+    else:
+        raise ValueError('Only the wiener filter has been implemented for denoising.')
+
+
 def migrate(self, mtype='stolt', vtaper=10, htaper=10, tmig=0, vel_fn=None, vel=1.68e8, nxpad=10,
             nearfield=False, verbose=0):
     """Dispatch on mtype exactly like _RadarDataFiltering.py:590-637; the callables are looked up on

@@ -11,9 +11,9 @@ SURVEY.md 8e).
 
 Same argument checks, same order of steps, same flags and same dtypes as the reference.  The index / resampling
 steps (hcrop, restack, reverse, nmo, crop - impdar_b200.processing) run on the device inside the
-same chain, so  hcrop -> restack -> reverse -> vbp -> hfilt -> ahfilt -> nmo -> crop -> migrate  is one upload and one
-download per profile.  Only denoise (scipy Wiener filter) and interp (GPS file I/O) stay host steps of the object's
-own methods and split the chain where the reference orders them (between nmo and crop).  One deviation: the reference
+same chain, so  hcrop -> restack -> reverse -> vbp -> hfilt -> ahfilt -> nmo -> denoise -> crop -> migrate  is one upload
+and one download per profile.  Only interp (GPS file I/O through impdar.lib.gpslib) stays a host step and splits the
+chain where the reference orders it (between denoise and crop).  One deviation: the reference
 applies hcrop while it is still checking arguments (process.py:111-119); here every argument is checked first, so a
 bad later argument leaves the profiles untouched.  There is no CPU fallback for the device steps.
 """
@@ -37,7 +37,7 @@ def _host_dtype_after(steps, in_dtype, dat=None):
     for name, args in steps:
         if name == 'migrate':
             dt = np.dtype(np.float32) if dt == np.float32 else np.dtype(np.float64)
-        elif name in ('restack', 'nmo'):
+        elif name in ('restack', 'nmo', 'denoise'):
             dt = np.dtype(np.float64)
         elif name == 'crop' and args[2] == 'pretrig' and isinstance(getattr(dat, 'trig', None), np.ndarray):
             dt = np.dtype(np.float64)
@@ -57,6 +57,8 @@ def _run_chain_on_device(dat, steps):
             _need(dat, 'nmo')(*args)
         elif name == 'crop':
             _need(dat, 'crop')(*args)
+        elif name == 'denoise':
+            _need(dat, 'denoise')(*args)
         elif name == 'vbp':
             dat.vertical_band_pass(*args)
         elif name == 'hfilt':
@@ -134,7 +136,7 @@ def process(RadarDataList, interp=None, rev=False, vbp=None, hfilt=None, ahfilt=
             hcrop=None, restack=None, denoise=None, migrate=None, n_streams=3, **kwargs):
     """Perform one or more processing steps on a list of RadarData; mirrors lib/process.py:72-197.
 
-    Returns True if a step was performed.  Every step except denoise / interp runs device resident."""
+    Returns True if a step was performed.  Every step except interp runs device resident."""
     # ---- argument checking, as the reference (process.py:101-134)
     if crop is not None:
         try:
@@ -190,22 +192,20 @@ def process(RadarDataList, interp=None, rev=False, vbp=None, hfilt=None, ahfilt=
         head.append(('ahfilt', ahfilt))
     if nmo is not None:
         head.append(('nmo', tuple(nmo)))
+    if denoise is not None:
+        head.append(('denoise', tuple(denoise)))
     tail = []
     if crop is not None:
         tail.append(('crop', crop))
     if migrate is not None:
         tail.append(('migrate', None))
-    host_between = denoise is not None or interp is not None
+    host_between = interp is not None
 
     if not host_between:
         run_device_chain(RadarDataList, head + tail, n_streams)
         return bool(head or tail)
 
     run_device_chain(RadarDataList, head, n_streams)
-
-    if denoise is not None:
-        for dat in RadarDataList:
-            _need(dat, 'denoise')(*denoise)
 
     if interp is not None:
         from impdar.lib.gpslib import interp as interpdeep   # the reference's own (process.py:24, :178)

@@ -61,6 +61,7 @@ class RadarData(object):
     winavg_hfilt = filtering.winavg_hfilt
     rangegain = filtering.rangegain
     agc = filtering.agc
+    denoise = filtering.denoise
     reverse = processing.reverse
     crop = processing.crop
     hcrop = processing.hcrop

@@ -13,6 +13,7 @@
  *   - RadarData/_RadarDataFiltering.py:19-90    adaptivehfilt
  *   - RadarData/_RadarDataFiltering.py:138-440  highpass / lowpass / horizontal_band_pass / winavg_hfilt
  *   - RadarData/_RadarDataProcessing.py:456-496 rangegain / agc
+ *   - RadarData/_RadarDataFiltering.py:552-587  denoise (Wiener)
  *   - RadarData/_RadarDataProcessing.py:20-637  reverse / crop / hcrop / restack / nmo / constant_space / elev_correct
  *
  * Conventions
@@ -259,6 +260,16 @@ int impdar_interp_cols_f32_f64(const float *x, double *y, int snum, int tnum_in,
                                int mode, void *stream);
 int impdar_interp_cols_f64(const double *x, double *y, int snum, int tnum_in, int tnum_out, const void *nodes,
                            int mode, void *stream);
+
+/* ------------------------------------------------------- denoise (_RadarDataFiltering.py:552-587) --- */
+/* scipy.signal.wiener(x, mysize=(vert_win, hor_win), noise): float64 box statistics, float64 output y (snum, tnum).
+ * estimate_noise != 0: noise = mean of the local variance (scipy's noise=None), `noise` is ignored.
+ * scratch: device, 16 bytes; after the call scratch[0] (double) holds the sum of the local variance and the int at
+ * byte 8 is 1 if some local variance is exactly zero (scipy divides by it; the reference raises ValueError).    */
+int impdar_wiener_f32(const float *x, double *y, int snum, int tnum, int vert_win, int hor_win, int estimate_noise,
+                      double noise, double *scratch, void *stream);
+int impdar_wiener_f64(const double *x, double *y, int snum, int tnum, int vert_win, int hor_win, int estimate_noise,
+                      double noise, double *scratch, void *stream);
 
 #ifdef __cplusplus
 }

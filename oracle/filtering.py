@@ -269,3 +269,38 @@ def agc(data, window=50, scaling_factor=50):
     maxamp[maxamp == 0] = 1.0e-6
     data *= (scaling_factor / np.atleast_2d(maxamp).transpose()).astype(data.dtype)
     return data
+
+
+def wiener(data, vert_win=1, hor_win=10, noise=None):
+    """denoise(ftype='wiener') (_RadarDataFiltering.py:573-582) = scipy.signal.wiener(data, (vert_win, hor_win), noise):
+    zero padded box statistics over rows [s - V//2, s + (V-1)//2] and columns [t - H//2, t + (H-1)//2]
+    (scipy.signal.correlate(..., 'same') with a ones window), local variance E[x^2] - mean^2 with the squares taken
+    in the input precision, noise = mean local variance unless given; float64 result.  scipy picks an FFT correlation
+    for these sizes, so the reference carries ~1e-16 relative rounding noise this direct summation does not."""
+    x = np.asarray(data)
+    if not np.issubdtype(x.dtype, np.floating):
+        x = x.astype(np.float64)
+    S, T = x.shape
+    V, H = int(vert_win), int(hor_win)
+    n = float(V * H)
+
+    def boxsum(img):
+        pad = np.zeros((S + V - 1, T + H - 1))
+        pad[V // 2:V // 2 + S, H // 2:H // 2 + T] = img
+        out = np.zeros((S, T))
+        for dv in range(V):
+            for dh in range(H):
+                out += pad[dv:dv + S, dh:dh + T]
+        return out
+
+    mean = boxsum(x) / n
+    var = boxsum(x ** 2) / n - mean ** 2
+    if noise is None:
+        noise = np.mean(var.reshape(-1))
+        if np.any(var == 0) and noise != 0:
+            raise ValueError('Could not compute variance, specify noise for denoise')
+    with np.errstate(divide='ignore', invalid='ignore'):
+        res = (x - mean)
+        res = res * (1 - noise / var)
+        res = res + mean
+    return np.where(var < noise, mean, res)

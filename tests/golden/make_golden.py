@@ -132,6 +132,21 @@ def run_siblings(tag, data, **mk):
     d = make_dat(data, **mk)
     quiet(d.agc, window=20, scaling_factor=50)
     save(tag + "_agc", data=data, out=d.data, window=20, scaling_factor=50, **geom(d))
+    run_denoise(tag, data, **mk)
+
+
+def run_denoise(tag, data, **mk):
+    """denoise(ftype='wiener') (_RadarDataFiltering.py:552-587): default window, a 2-D window, an even x even
+    window, a given noise power; float32 input as well (scipy squares in the input precision)."""
+    for name, dtype, kw in (("default", np.float64, {}), ("v3h5", np.float64, dict(vert_win=3, hor_win=5)),
+                            ("v4h2", np.float64, dict(vert_win=4, hor_win=2)),
+                            ("noise", np.float64, dict(vert_win=3, hor_win=7, noise=0.4)),
+                            ("f32_v3h5", np.float32, dict(vert_win=3, hor_win=5))):
+        d = make_dat(data.astype(dtype) + (3.0 if "f32" in name else 0.0), **mk)
+        x = d.data.copy()
+        quiet(d.denoise, **kw)
+        save("%s_denoise_%s" % (tag, name), data=x, out=d.data, vert_win=kw.get("vert_win", 1),
+             hor_win=kw.get("hor_win", 10), noise=kw.get("noise", np.nan), **geom(d))
 
 
 def run_lateral():
@@ -161,6 +176,10 @@ def main():
     slow = "--slow" in sys.argv
     if "--only-lateral" in sys.argv:
         run_lateral()
+        return
+    if "--only-denoise" in sys.argv:
+        rng = np.random.default_rng(17)
+        run_denoise("r96x160", rng.standard_normal((96, 160)) + 2.0, tt0_us=0.001)
         return
     if "--only-siblings" in sys.argv:
         rng = np.random.default_rng(17)

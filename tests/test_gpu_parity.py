@@ -339,3 +339,34 @@ def test_winavg_long_rows_vs_oracle():
     want = of.winavg_hfilt(d.data[:, :], d.travel_time, 201)
     d.winavg_hfilt(201)
     assert _report("winavg 16x30000", d.data, want) < 1e-12
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_denoise_"))
+def test_denoise_golden(name):
+    g = load_golden(name)
+    noise = None if np.isnan(g["noise"]) else float(g["noise"])
+    d = dat_from_golden(g)
+    d.denoise(vert_win=int(g["vert_win"]), hor_win=int(g["hor_win"]), noise=noise)
+    assert isinstance(d.data, np.ndarray) and d.data.dtype == np.float64 and d.data.shape == g["out"].shape
+    assert _report(name, d.data, g["out"]) < (1e-6 if g["data"].dtype == np.float32 else 1e-12)
+
+
+def test_denoise_large_vs_oracle_and_errors():
+    from oracle import filtering as of
+    import torch
+    d = synthetic_dat(700, 1300, seed=41)
+    want = of.wiener(d.data, 5, 9)
+    x = d.data.copy()
+    d.denoise(vert_win=5, hor_win=9)
+    assert _report("denoise 700x1300 f32", d.data, want) < 1e-12
+    d = synthetic_dat(64, 96, seed=42)
+    d.data = torch.from_numpy(d.data).cuda()                     # device lane: stays on the GPU, float32 in -> float32 out
+    d.denoise(noise=0.3)
+    assert isinstance(d.data, torch.Tensor) and d.data.is_cuda and d.data.dtype == torch.float32
+    d = synthetic_dat(32, 64, seed=43)
+    d.data[:] = 1.0
+    d.data[:, 40:] = np.arange(32, dtype=np.float32)[:, None]    # zero local variance in the left half, not overall
+    with pytest.raises(ValueError):
+        d.denoise(vert_win=1, hor_win=3)
+    with pytest.raises(ValueError):
+        d.denoise(ftype='dummy')

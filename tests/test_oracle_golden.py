@@ -121,3 +121,20 @@ def test_gains(name):
         trig = g["trig"] if g["trig"].ndim else int(g["trig"])
         out = of.rangegain(g["data"], g["travel_time"], trig, float(g["slope"]))
     assert np.array_equal(out, g["out"])
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_denoise_"))
+def test_denoise_wiener(name):
+    """The reference's scipy.signal.wiener runs an FFT correlation (complex64 for float32 input), the oracle sums the
+    window directly in float64: agreement to rounding noise of the reference (1e-15 float64, 2e-7 float32 input)."""
+    g = load_golden(name)
+    noise = None if np.isnan(g["noise"]) else float(g["noise"])
+    out = of.wiener(g["data"], int(g["vert_win"]), int(g["hor_win"]), noise)
+    assert out.dtype == np.float64 and out.shape == g["out"].shape
+    rel = np.linalg.norm(out - g["out"]) / np.linalg.norm(g["out"])
+    assert rel < (1e-6 if g["data"].dtype == np.float32 else 1e-13)
+
+
+def test_denoise_zero_variance_raises_like_reference():
+    with pytest.raises(ValueError):
+        of.wiener(np.pad(np.ones((4, 40)), ((0, 4), (0, 0))) + np.arange(8)[:, None] * np.r_[np.zeros(20), np.ones(20)], 1, 3)

@@ -28,8 +28,8 @@ def test_argument_checks_like_reference():
         proc.process([_dat()], vbp=3)
     with pytest.raises(ValueError):
         proc.process([_dat()], interp=('x',))
-    with pytest.raises(NotImplementedError):                    # denoise is a host step the stand-in does not carry
-        proc.process([_dat()], denoise=(1, 2))
+    with pytest.raises(Exception):                              # interp needs ImpDAR's gpslib and a GPS file
+        proc.process([_dat()], interp=(10., 'no_such_gps_file.mat'))
 
 
 def test_step_order_and_chain_split(monkeypatch):
@@ -38,7 +38,6 @@ def test_step_order_and_chain_split(monkeypatch):
     calls = []
     monkeypatch.setattr(proc, 'run_device_chain', lambda dats, steps, n: calls.append([s[0] for s in steps]))
     d = _dat()
-    d.denoise = lambda *a: calls.append('denoise')
     assert proc.process([d], vbp=(2, 10), hfilt=(0, 40), ahfilt=10, migrate=True)
     assert calls == [['vbp', 'hfilt', 'ahfilt', 'migrate']]
     del calls[:]
@@ -47,7 +46,7 @@ def test_step_order_and_chain_split(monkeypatch):
     assert calls == [['hcrop', 'restack', 'rev', 'vbp', 'ahfilt', 'nmo', 'crop', 'migrate']]
     del calls[:]
     assert proc.process([d], vbp=(2, 10), nmo=(10., 1.69e8), denoise=(3, 3), crop=(0.1, 'top', 'twtt'), migrate=True)
-    assert calls == [['vbp', 'nmo'], 'denoise', ['crop', 'migrate']]
+    assert calls == [['vbp', 'nmo', 'denoise', 'crop', 'migrate']]
 
 
 def test_chain_result_dtypes_follow_reference():
