@@ -15,6 +15,17 @@
 
 namespace impdar {
 
+constexpr int IO_ROWS = 4;   // rows per thread in the streaming kernels below
+
+static inline dim3 io_grid(int ncols, int nrows, int batch = 1) {
+    const int gx = min((ncols + 255) / 256, 64);
+    const int row_groups = (nrows + IO_ROWS - 1) / IO_ROWS;
+    int gy = (8 * num_sms() + gx - 1) / gx;          // ~8 CTAs of 256 threads per SM over the whole grid
+    if (gy > row_groups) gy = row_groups;
+    if (gy < 1) gy = 1;
+    return dim3((unsigned)gx, (unsigned)gy, (unsigned)batch);
+}
+
 // ------------------------------------------------------------------------------------------------ block copy
 // y[b, i, j] = x[b, r0 + i, flip ? c0 + (nc - 1 - j) : c0 + j]
 template <typename T>
@@ -23,11 +34,19 @@ __global__ void __launch_bounds__(256) crop_block_kernel(const T *__restrict__ x
     const int b = blockIdx.z;
     const T *xb = x + (size_t)b * S * T_;
     T *yb = y + (size_t)b * nr * nc;
-    for (int i = blockIdx.y; i < nr; i += gridDim.y) {
-        const T *src = xb + (size_t)(r0 + i) * T_ + c0;
-        T *dst = yb + (size_t)i * nc;
-        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nc; j += gridDim.x * blockDim.x)
-            dst[j] = src[flip ? (nc - 1 - j) : j];
+    // IO_ROWS rows per thread: independent loads in flight (a 4-byte element per thread and row would leave the
+    // memory system idle: ~8 KB in flight per SM against the ~40 KB the HBM latency needs)
+    for (int i0 = blockIdx.y * IO_ROWS; i0 < nr; i0 += gridDim.y * IO_ROWS) {
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nc; j += gridDim.x * blockDim.x) {
+            const int js = flip ? (nc - 1 - j) : j;
+            T v[IO_ROWS];
+#pragma unroll
+            for (int k = 0; k < IO_ROWS; ++k)
+                if (i0 + k < nr) v[k] = xb[(size_t)(r0 + i0 + k) * T_ + c0 + js];
+#pragma unroll
+            for (int k = 0; k < IO_ROWS; ++k)
+                if (i0 + k < nr) yb[(size_t)(i0 + k) * nc + j] = v[k];
+        }
     }
 }
 
@@ -40,7 +59,7 @@ static int crop_block(const T *x, T *y, int S, int T_, int batch, int r0, int r1
     const int nr = r1 - r0, nc = c1 - c0;
     if (nr == 0 || nc == 0) return IMPDAR_B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)min((nc + 255) / 256, 64), (unsigned)min(nr, 4 * num_sms()), (unsigned)batch);
+    dim3 grid = io_grid(nc, nr, batch);
     ktimer_begin("crop_block_kernel", st);
     crop_block_kernel<T><<<grid, 256, 0, st>>>(x, y, S, T_, nr, nc, r0, c0, flip);
     ktimer_end(st);
@@ -56,9 +75,16 @@ __global__ void __launch_bounds__(256) shift_traces_kernel(const TI *__restrict_
     const TO nanv = (TO)__longlong_as_double(0x7ff8000000000000LL);
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T_; t += gridDim.x * blockDim.x) {
         const int sh = shift[t];
-        for (int i = blockIdx.y; i < S_out; i += gridDim.y) {
-            const long long src = (long long)i + sh;
-            y[(size_t)i * T_ + t] = (src >= 0 && src < S_in) ? (TO)x[(size_t)src * T_ + t] : nanv;
+        for (int i0 = blockIdx.y * IO_ROWS; i0 < S_out; i0 += gridDim.y * IO_ROWS) {
+            TO v[IO_ROWS];
+#pragma unroll
+            for (int k = 0; k < IO_ROWS; ++k) {
+                const long long src = (long long)i0 + k + sh;
+                v[k] = (i0 + k < S_out && src >= 0 && src < S_in) ? (TO)x[(size_t)src * T_ + t] : nanv;
+            }
+#pragma unroll
+            for (int k = 0; k < IO_ROWS; ++k)
+                if (i0 + k < S_out) y[(size_t)(i0 + k) * T_ + t] = v[k];
         }
     }
 }
@@ -69,7 +95,7 @@ static int shift_traces(const TI *x, TO *y, int S_in, int T_, int S_out, const i
     IMPDAR_CHECK_ARG(S_in >= 1 && T_ >= 1 && S_out >= 0, "shift_traces: bad shape");
     if (S_out == 0) return IMPDAR_B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)min((T_ + 255) / 256, 64), (unsigned)min(S_out, 4 * num_sms()));
+    dim3 grid = io_grid(T_, S_out);
     ktimer_begin("shift_traces_kernel", st);
     shift_traces_kernel<TI, TO><<<grid, 256, 0, st>>>(x, y, S_in, T_, S_out, shift);
     ktimer_end(st);
@@ -208,11 +234,21 @@ __device__ __forceinline__ double interp_value(const InterpNode &nd, TI ylo, TI 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) interp_rows_kernel(const TI *__restrict__ x, TO *__restrict__ y, int T_,
                                                           int S_out, const InterpNode *__restrict__ nodes, int mode) {
-    for (int i = blockIdx.y; i < S_out; i += gridDim.y) {
-        const InterpNode nd = nodes[i];
-        const TI *lo = x + (size_t)nd.lo * T_, *hi = x + (size_t)nd.hi * T_;
-        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T_; t += gridDim.x * blockDim.x)
-            y[(size_t)i * T_ + t] = (TO)interp_value<TI>(nd, lo[t], hi[t], mode);
+    for (int i0 = blockIdx.y * IO_ROWS; i0 < S_out; i0 += gridDim.y * IO_ROWS) {
+        InterpNode nd[IO_ROWS];
+#pragma unroll
+        for (int k = 0; k < IO_ROWS; ++k) nd[k] = nodes[min(i0 + k, S_out - 1)];
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T_; t += gridDim.x * blockDim.x) {
+            TI lo[IO_ROWS], hi[IO_ROWS];
+#pragma unroll
+            for (int k = 0; k < IO_ROWS; ++k) {
+                lo[k] = x[(size_t)nd[k].lo * T_ + t];
+                hi[k] = x[(size_t)nd[k].hi * T_ + t];
+            }
+#pragma unroll
+            for (int k = 0; k < IO_ROWS; ++k)
+                if (i0 + k < S_out) y[(size_t)(i0 + k) * T_ + t] = (TO)interp_value<TI>(nd[k], lo[k], hi[k], mode);
+        }
     }
 }
 
@@ -223,9 +259,17 @@ __global__ void __launch_bounds__(256) interp_cols_kernel(const TI *__restrict__
                                                           int mode) {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < T_out; j += gridDim.x * blockDim.x) {
         const InterpNode nd = nodes[j];
-        for (int s = blockIdx.y; s < S; s += gridDim.y) {
-            const TI *row = x + (size_t)s * T_in;
-            y[(size_t)s * T_out + j] = (TO)interp_value<TI>(nd, row[nd.lo], row[nd.hi], mode);
+        for (int s0 = blockIdx.y * IO_ROWS; s0 < S; s0 += gridDim.y * IO_ROWS) {
+            TI lo[IO_ROWS], hi[IO_ROWS];
+#pragma unroll
+            for (int k = 0; k < IO_ROWS; ++k) {
+                const TI *row = x + (size_t)min(s0 + k, S - 1) * T_in;
+                lo[k] = row[nd.lo];
+                hi[k] = row[nd.hi];
+            }
+#pragma unroll
+            for (int k = 0; k < IO_ROWS; ++k)
+                if (s0 + k < S) y[(size_t)(s0 + k) * T_out + j] = (TO)interp_value<TI>(nd, lo[k], hi[k], mode);
         }
     }
 }
@@ -236,7 +280,7 @@ static int interp_rows(const TI *x, TO *y, int S_in, int T_, int S_out, const vo
     IMPDAR_CHECK_ARG(S_in >= 2 && T_ >= 1 && S_out >= 0 && (mode == 0 || mode == 1), "interp_rows: bad argument");
     if (S_out == 0) return IMPDAR_B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)min((T_ + 255) / 256, 64), (unsigned)min(S_out, 4 * num_sms()));
+    dim3 grid = io_grid(T_, S_out);
     ktimer_begin("interp_rows_kernel", st);
     interp_rows_kernel<TI, TO><<<grid, 256, 0, st>>>(x, y, T_, S_out, (const InterpNode *)nodes, mode);
     ktimer_end(st);
@@ -250,7 +294,7 @@ static int interp_cols(const TI *x, TO *y, int S, int T_in, int T_out, const voi
     IMPDAR_CHECK_ARG(S >= 1 && T_in >= 2 && T_out >= 0 && (mode == 0 || mode == 1), "interp_cols: bad argument");
     if (T_out == 0) return IMPDAR_B200_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)min((T_out + 255) / 256, 64), (unsigned)min(S, 4 * num_sms()));
+    dim3 grid = io_grid(T_out, S);
     ktimer_begin("interp_cols_kernel", st);
     interp_cols_kernel<TI, TO><<<grid, 256, 0, st>>>(x, y, S, T_in, T_out, (const InterpNode *)nodes, mode);
     ktimer_end(st);
@@ -268,15 +312,21 @@ size_t impdar_interp_node_bytes(void) { return sizeof(InterpNode); }
 
 int impdar_crop_f32(const float *x, float *y, int snum, int tnum, int batch, int r0, int r1, int c0, int c1,
                     int flip_lr, void *stream) {
-    return crop_block<float>(x, y, snum, tnum, batch, r0, r1, c0, c1, flip_lr, stream);
+    return impdar_crop_bytes(x, y, snum, tnum, batch, r0, r1, c0, c1, flip_lr, 4, stream);
 }
 int impdar_crop_f64(const double *x, double *y, int snum, int tnum, int batch, int r0, int r1, int c0, int c1,
                     int flip_lr, void *stream) {
-    return crop_block<double>(x, y, snum, tnum, batch, r0, r1, c0, c1, flip_lr, stream);
+    return impdar_crop_bytes(x, y, snum, tnum, batch, r0, r1, c0, c1, flip_lr, 8, stream);
 }
 
 int impdar_crop_bytes(const void *x, void *y, int snum, int tnum, int batch, int r0, int r1, int c0, int c1,
                       int flip_lr, int elem_bytes, void *stream) {
+    // 128-bit lanes whenever every row segment starts and ends on a 16-byte boundary
+    if (!flip_lr && elem_bytes >= 1 && elem_bytes < 16 && 16 % elem_bytes == 0) {
+        const int per = 16 / elem_bytes;
+        if (tnum % per == 0 && c0 % per == 0 && c1 % per == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0)
+            return crop_block<uint4>((const uint4 *)x, (uint4 *)y, snum, tnum / per, batch, r0, r1, c0 / per, c1 / per, 0, stream);
+    }
     switch (elem_bytes) {
         case 1: return crop_block<uint8_t>((const uint8_t *)x, (uint8_t *)y, snum, tnum, batch, r0, r1, c0, c1, flip_lr, stream);
         case 2: return crop_block<uint16_t>((const uint16_t *)x, (uint16_t *)y, snum, tnum, batch, r0, r1, c0, c1, flip_lr, stream);
