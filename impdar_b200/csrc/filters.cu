@@ -381,6 +381,194 @@ __global__ void __launch_bounds__(256) ahfilt_strip_kernel(const T *__restrict__
     }
 }
 
+// Sliding-window kernel (for windows too wide for the strip kernel's prefix buffer; testing hook 3): one WARP owns a strip of WS output traces and a chunk of R sample rows; no block-level
+// synchronisation at all.  Per row the window sum of the strip's first trace is reduced cooperatively, then the sums of
+// the following traces come from the differences sum(i) - sum(i-1) = (elements entering) - (elements leaving) - in the
+// interior exactly x[i+h-1] - x[i-h] - accumulated by a float64 warp scan, 64 traces per step (two independent scans in
+// flight) with the running sum carried in a register.  Window means go into the warp's own ring of the last seven mean
+// rows in shared memory; a row is written out as soon as its 7-tap neighbourhood is complete.  Measured on B200
+// (profiles/r01g_ahfilt_slide_*.txt): 1.13-1.20 ms for 8 x 2048 x 8192 at w = 1000 against 0.90 ms for the strip kernel -
+// the strip-start window sum (w / 32 loads per row and warp) and the 40 double shuffles per 256 traces cost as much as
+// the strip kernel's block-wide prefix sums - so the strip kernel stays the default where it applies.
+template <typename T>
+__device__ __forceinline__ double ah_delta(const T *__restrict__ xr, int i, int Tn, int w, int tail_lo) {
+    int lo, hi, lp, hp;
+    ahfilt_window(i, Tn, w, tail_lo, lo, hi);
+    ahfilt_window(i - 1, Tn, w, tail_lo, lp, hp);
+    double d = 0.0;
+    for (int k = hp; k < hi; ++k) d += (double)xr[k];
+    for (int k = hi; k < hp; ++k) d -= (double)xr[k];
+    for (int k = lp; k < lo; ++k) d -= (double)xr[k];
+    for (int k = lo; k < lp; ++k) d += (double)xr[k];
+    return d;
+}
+
+__device__ __forceinline__ double warp_scan_incl(double v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+
+template <typename T, int NE>   // strip width WS = 32 * NE traces; lane l owns traces c0 + 32 e + l, e < NE
+__global__ void __launch_bounds__(256) ahfilt_slide_kernel(const T *__restrict__ x, T *__restrict__ y, int S, int Tn,
+                                                           int w, int tail_lo, const double *__restrict__ taper, int R) {
+    constexpr int WS = 32 * NE;
+    extern __shared__ double smem_d[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    T *ring = reinterpret_cast<T *>(smem_d) + (size_t)warp * 7 * WS;   // [7][WS], this warp's own
+    const int c0 = (blockIdx.x * nw + warp) * WS;
+    if (c0 >= Tn) return;
+    const int c1 = min(Tn, c0 + WS);
+    const T *xb = x + (long long)blockIdx.z * S * Tn;
+    T *yb = y + (long long)blockIdx.z * S * Tn;
+    const int s_begin = blockIdx.y * R, s_end = min(S, s_begin + R);
+    const int r0 = max(0, s_begin - 3), r1 = min(S - 1, s_end + 2);
+    int next_out = s_begin;
+    int lo0, hi0;
+    ahfilt_window(c0, Tn, w, tail_lo, lo0, hi0);
+    // Row-invariant description of every trace this lane owns: sum(i) - sum(i-1) = x[ent] - x[lev] (either may be absent:
+    // -1); the few traces where a window bound moves by more than one element (regime changes) take the general path.
+    int ent[NE], lev[NE];
+    double wv[NE];
+    unsigned rare = 0;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const int i = c0 + 32 * e + lane;
+        ent[e] = lev[e] = -1;
+        wv[e] = 0.0;
+        if (i < c1) {
+            int lo, hi, lp, hp;
+            ahfilt_window(i, Tn, w, tail_lo, lo, hi);
+            wv[e] = __drcp_rn((double)(hi - lo));   // inf for an empty window: 0 * inf = NaN like np.mean of an empty slice
+            if (i > c0) {
+                ahfilt_window(i - 1, Tn, w, tail_lo, lp, hp);
+                if (hi == hp + 1) ent[e] = hp;
+                else if (hi != hp) rare |= 1u << e;
+                if (lo == lp + 1) lev[e] = lp;
+                else if (lo != lp) rare |= 1u << e;
+            }
+        }
+    }
+    const bool any_rare = __any_sync(0xffffffffu, rare != 0);
+
+    for (int r = r0; r <= r1; ++r) {
+        const T *xr = xb + (long long)r * Tn;
+        // ---- every load of this row first (independent: they overlap), then the arithmetic
+        T vin[NE], vout[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            vin[e] = ent[e] >= 0 ? xr[ent[e]] : (T)0;
+            vout[e] = lev[e] >= 0 ? xr[lev[e]] : (T)0;
+        }
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+        {
+            int k = lo0 + lane;
+            for (; k + 96 < hi0; k += 128) {
+                const T a0 = xr[k], a1 = xr[k + 32], a2 = xr[k + 64], a3 = xr[k + 96];
+                p0 += (double)a0; p1 += (double)a1; p2 += (double)a2; p3 += (double)a3;
+            }
+            for (; k < hi0; k += 32) p0 += (double)xr[k];
+        }
+        double d[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) d[e] = (double)vin[e] - (double)vout[e];
+        if (any_rare) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e)
+                if (rare & (1u << e)) d[e] = ah_delta(xr, c0 + 32 * e + lane, Tn, w, tail_lo);
+        }
+        // window sum of the strip's first trace: the scan starts from it
+        const double s0 = warp_sum((p0 + p1) + (p2 + p3));
+        if (lane == 0) d[0] = s0;
+        // ---- NE independent warp scans (interleaved by the unroll), then the strip-wide offsets
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const double u = __shfl_up_sync(0xffffffffu, d[e], o);
+                if (lane >= o) d[e] += u;
+            }
+        }
+        T *mrow = ring + (r % 7) * WS;
+        double carry = 0.0;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const double tot = __shfl_sync(0xffffffffu, d[e], 31);
+            const double sum = carry + d[e];
+            carry += tot;
+            if (c0 + 32 * e + lane < c1) mrow[32 * e + lane] = (T)(sum * wv[e]);
+        }
+        __syncwarp();
+        while (next_out < s_end && (next_out + 3 <= r || r == S - 1)) {
+            const int s = next_out++;
+            const double tp = taper[s];
+            const T *xs = xb + (long long)s * Tn + c0;
+            T *ys = yb + (long long)s * Tn + c0;
+            T xv[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) xv[e] = (c0 + 32 * e + lane < c1) ? xs[32 * e + lane] : (T)0;
+            if (s >= 3 && s + 3 < S) {
+                const T *q0 = ring + ((s - 3) % 7) * WS, *q1 = ring + ((s - 2) % 7) * WS, *q2 = ring + ((s - 1) % 7) * WS;
+                const T *q3 = ring + (s % 7) * WS, *q4 = ring + ((s + 1) % 7) * WS, *q5 = ring + ((s + 2) % 7) * WS;
+                const T *q6 = ring + ((s + 3) % 7) * WS;
+                const T tpT = (T)tp;
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const int c = 32 * e + lane;
+                    const T f = (T)0.0625 * (q0[c] + q6[c]) + (T)0.125 * (q1[c] + q5[c]) + (T)0.1875 * (q2[c] + q4[c]) +
+                                (T)0.25 * q3[c];
+                    if (c0 + c < c1) ys[c] = xv[e] - f * tpT;
+                }
+            } else {
+                // edges: the kernel on the odd-extended mean trace, folded onto real rows
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const int c = 32 * e + lane;
+                    if (c0 + c >= c1) continue;
+                    double f = 0.0;
+#pragma unroll
+                    for (int j = -3; j <= 3; ++j) {
+                        const double cj = (double)(4 - (j < 0 ? -j : j)) / 16.0;
+                        const int q = s + j;
+                        if (q < 0) f += cj * (2.0 * (double)ring[c] - (double)ring[((-q) % 7) * WS + c]);
+                        else if (q >= S) f += cj * (2.0 * (double)ring[((S - 1) % 7) * WS + c] -
+                                                    (double)ring[((2 * (S - 1) - q) % 7) * WS + c]);
+                        else f += cj * (double)ring[(q % 7) * WS + c];
+                    }
+                    ys[c] = (T)((double)xv[e] - f * tp);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T, int NE>
+static int launch_ahfilt_slide(const T *x, T *y, int S, int Tn, int batch, int w, int tail_lo, const double *taper, int R,
+                               cudaStream_t st) {
+    constexpr int WS = 32 * NE;
+    const int nstrips = (Tn + WS - 1) / WS;
+    const int nw = nstrips < 8 ? nstrips : 8;
+    const size_t smem = (size_t)nw * 7 * WS * sizeof(T);
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (8 * 7 * WS * sizeof(T) > 48 * 1024)
+            IMPDAR_CUDA(cudaFuncSetAttribute(ahfilt_slide_kernel<T, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(8 * 7 * WS * sizeof(T))));
+        attr_done = true;
+    }
+    dim3 grid((nstrips + nw - 1) / nw, (S + R - 1) / R, batch);
+    IMPDAR_CHECK_ARG(batch <= 65535 && grid.y <= 65535, "ahfilt: batch too large");
+    ktimer_begin("ahfilt_slide_kernel", st);
+    ahfilt_slide_kernel<T, NE><<<grid, nw * 32, smem, st>>>(x, y, S, Tn, w, tail_lo, taper, R);
+    ktimer_end(st);
+    IMPDAR_LAUNCH_CHECK();
+    return IMPDAR_B200_OK;
+}
+
 // ------------------------------------------------------------------------------------------ filtfilt
 // Software-pipelined recurrence over n strided samples: the next block of FF_U inputs is in flight while the current
 // block runs through the (serial, fp64-pipe bound) recurrence, so the HBM latency hides behind 21 DFMA per sample.
@@ -590,7 +778,7 @@ static int hfilt_impl(const T *x, T *y, int S, int Tn, int batch, int htr1, int 
 }
 
 static const size_t AHFILT_SMEM_LIMIT = 200 * 1024;
-static int g_ahfilt_force_rowwise = 0;  // testing hook: 1 = always the one-row-per-CTA kernel
+static int g_ahfilt_force_rowwise = 0;  // testing hook: 0 = auto (strip kernel, else warp-sliding), 1 = one-row-per-CTA kernel, 3 = warp-sliding kernel
 
 template <typename T>
 static int ahfilt_impl(const T *x, T *y, int S, int Tn, int batch, int w, const double *taper, void *ws,
@@ -603,8 +791,26 @@ static int ahfilt_impl(const T *x, T *y, int S, int Tn, int batch, int w, const 
     // python slice start of data[:, tnum - w : tnum]
     int tail_lo = Tn - w;
     if (tail_lo < 0) tail_lo = (tail_lo + Tn < 0) ? 0 : tail_lo + Tn;
-    // strip kernel whenever the prefix buffer of one strip (W + ~w columns) and the 7-row ring fit in shared memory
-    {
+    // the warp-sliding kernel: any shape and window; takes the shapes the strip kernel does not cover (hook 3 forces it)
+    auto run_slide = [&]() -> int {
+        int WS = 256, R = 64;
+        while (WS > 64 && WS / 2 >= Tn) WS /= 2;
+        auto warps = [&](int ws, int r) { return (long long)batch * ((S + r - 1) / r) * ((Tn + ws - 1) / ws); };
+        const long long want = (long long)num_sms() * 16;
+        if (warps(WS, R) < want) R = 32;
+        if (warps(WS, R) < want && WS > 128) WS /= 2;
+        if (warps(WS, R) < want) R = 16;
+        if (const char *e = getenv("IMPDAR_AH_WS")) WS = atoi(e);   // development A/B switches
+        if (const char *e = getenv("IMPDAR_AH_R")) R = atoi(e);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (WS >= 256) return launch_ahfilt_slide<T, 8>(x, y, S, Tn, batch, w, tail_lo, taper, R, st);
+        if (WS >= 128) return launch_ahfilt_slide<T, 4>(x, y, S, Tn, batch, w, tail_lo, taper, R, st);
+        return launch_ahfilt_slide<T, 2>(x, y, S, Tn, batch, w, tail_lo, taper, R, st);
+    };
+    if (g_ahfilt_force_rowwise == 3) return run_slide();
+    // default: the prefix-sum strip kernel, whenever the prefix buffer of one strip (W + ~w columns) and the 7-row ring fit
+    // in shared memory
+    if (g_ahfilt_force_rowwise != 1) {
         int W = (sizeof(T) == 4) ? 2048 : 1024;
         if (W > Tn) W = ((Tn + 31) / 32) * 32;
         const int h = w / 2;
@@ -625,7 +831,7 @@ static int ahfilt_impl(const T *x, T *y, int S, int Tn, int batch, int w, const 
             if (L1 - L0 > nmax) nmax = L1 - L0;
         }
         const size_t smem_strip = (size_t)(4096 + 256 + 256 + 8) * sizeof(double) + (size_t)7 * W * sizeof(T);
-        if (nmax <= 4096 && g_ahfilt_force_rowwise == 0) {
+        if (nmax <= 4096) {
             static bool attr_done = false;
             if (!attr_done) {
                 IMPDAR_CUDA(cudaFuncSetAttribute(ahfilt_strip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -640,6 +846,7 @@ static int ahfilt_impl(const T *x, T *y, int S, int Tn, int batch, int w, const 
             IMPDAR_LAUNCH_CHECK();
             return IMPDAR_B200_OK;
         }
+        if (g_ahfilt_force_rowwise == 0) return run_slide();   // windows wider than the strip buffer
     }
     const long long rows = (long long)batch * S;
     const size_t need_smem = (size_t)(Tn + 1) * sizeof(double);
@@ -704,7 +911,7 @@ size_t impdar_ahfilt_workspace_bytes(int S, int T, int batch) {
     return (size_t)num_sms() * 4 * (size_t)(T + 1) * sizeof(double);
 }
 int impdar_ahfilt_force_rowwise(int on) {
-    g_ahfilt_force_rowwise = on ? 1 : 0;
+    g_ahfilt_force_rowwise = (on == 3) ? 3 : (on ? 1 : 0);
     return IMPDAR_B200_OK;
 }
 int impdar_ahfilt_f32(const float *x, float *y, int S, int T, int batch, int w, const double *taper, void *ws,

@@ -71,7 +71,8 @@ int impdar_hfilt_f64(const double *x, double *y, int snum, int tnum, int batch, 
  * filtfilt([.25]*4, 1, .) amounts to on the odd-extended mean trace, the exp taper, the subtraction.
  * Requires snum > 12 (scipy's padlen).  workspace: impdar_ahfilt_workspace_bytes() bytes (may be 0). */
 size_t impdar_ahfilt_workspace_bytes(int snum, int tnum, int batch);
-/* Testing hook: 1 forces the one-row-per-CTA kernel instead of the strip kernel (rolling 7-row ring).   */
+/* Testing hook: 0 = auto (prefix-sum strip kernel; warp-sliding kernel for windows wider than its buffer), 1 = the
+ * one-row-per-CTA kernel, 3 = the warp-sliding kernel.                                                              */
 int impdar_ahfilt_force_rowwise(int on);
 int impdar_ahfilt_f32(const float *x, float *y, int snum, int tnum, int batch, int window_size,
                       const double *taper, void *workspace, size_t workspace_bytes, void *stream);

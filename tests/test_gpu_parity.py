@@ -162,10 +162,12 @@ def test_ahfilt_golden(name):
 
 
 @pytest.mark.parametrize("S,T,w", [(300, 5000, 7), (300, 5000, 100), (130, 5000, 1001), (130, 5000, 4000),
-                                   (70, 3000, 6000), (200, 8192, 1000), (64, 2500, 2)])
+                                   (70, 3000, 6000), (200, 8192, 1000), (64, 2500, 2), (40, 700, 1), (40, 700, 0),
+                                   (33, 130, 129), (33, 130, 130), (33, 130, 131), (50, 65, 3), (20, 2049, 64)])
 def test_ahfilt_strip_vs_oracle(S, T, w):
-    """The strip kernel (rolling 7-row ring, fp64 prefix sums per row segment) against the float64 oracle on shapes with
-    several strips, odd / even / oversized windows and a DC offset; and against the one-row-per-CTA kernel."""
+    """The default path (prefix-sum strip kernel with a rolling 7-row ring; warp-sliding kernel for windows wider than
+    its buffer) against the float64 oracle on shapes with several strips, odd / even / oversized windows and a DC
+    offset; the warp-sliding kernel and the one-row-per-CTA kernel forced through the testing hook, same oracle."""
     import torch
     from oracle import filtering as of
     from impdar_b200 import _lib, filtering as fl
@@ -177,15 +179,18 @@ def test_ahfilt_strip_vs_oracle(S, T, w):
     xd = torch.from_numpy(x).cuda()
     got = fl.adaptivehfilt_device(xd, 'f32', tp, w).cpu().numpy()
     lib = _lib.load()
-    lib.impdar_ahfilt_force_rowwise(1)
-    try:
-        got_row = fl.adaptivehfilt_device(xd, 'f32', tp, w).cpu().numpy()
-    finally:
-        lib.impdar_ahfilt_force_rowwise(0)
+    others = []
+    for mode in (1, 3):                     # 1 = one-row-per-CTA kernel, 3 = warp-sliding kernel
+        lib.impdar_ahfilt_force_rowwise(mode)
+        try:
+            others.append(fl.adaptivehfilt_device(xd, 'f32', tp, w).cpu().numpy())
+        finally:
+            lib.impdar_ahfilt_force_rowwise(0)
     m = np.isfinite(want)
     assert np.array_equal(np.isfinite(got), m)
-    assert _report("ahfilt strip %dx%d w%d" % (S, T, w), got[m], want[m]) < TOL
-    assert rel_l2(got_row[m], want[m]) < TOL
+    assert _report("ahfilt %dx%d w%d" % (S, T, w), got[m], want[m]) < TOL
+    for o in others:
+        assert np.array_equal(np.isfinite(o), m) and rel_l2(o[m], want[m]) < TOL
     # batch of two profiles == the profiles one by one
     xb = torch.stack([xd, xd.flip(0).contiguous()])
     gb = fl.adaptivehfilt_device(xb, 'f32', tp, w)
