@@ -528,21 +528,27 @@ __global__ void __launch_bounds__(256) kirch_table_fixup_kernel(const __grid_con
                                                                 const int *__restrict__ amb_list,
                                                                 const int *__restrict__ amb_count) {
     const int lane = threadIdx.x & 31;
-    const long long nblk = (tp.x_end - tp.x_begin + 31) / 32;
-    const long long nitems = (long long)(*amb_count) * nblk;
-    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long it = wid; it < nitems; it += nwarps) {
-        const int e = amb_list[it / nblk];
+    const int nblk = (tp.x_end - tp.x_begin + 31) / 32;
+    const int count = *amb_count;
+    const int wid = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+    // Entries outside this launch's row range are skipped with one load each (row-chunked launches would otherwise
+    // walk the whole (entry, block) space every time); an in-range entry is spread over `split` warps.
+    const int split = 8;
+    for (long long it = wid; it < (long long)count * split; it += nwarps) {
+        const int e = amb_list[it / split];
         const int ti = e / tp.A1, m = e % tp.A1;
-        const int xi = tp.x_begin + (int)(it % nblk) * 32 + lane;
-        if (xi >= tp.x_end || ti < tp.s_begin || ti >= tp.s_end) continue;
-        const double dxi = gp.dist[xi];
-        float term = 0.f;
-        if (xi - m >= 0) term += exact_term<NEAR>(gp, ti, xi - m, dxi);
-        if (m != 0 && xi + m < tp.T) term += exact_term<NEAR>(gp, ti, xi + m, dxi);
-        if (term != 0.f) atomicAdd(&tp.out[(size_t)ti * tp.ldo + (xi - tp.x_begin)], term);
-        if (tp.stats) atomicAdd(&tp.stats[1], 1ull);
+        if (ti < tp.s_begin || ti >= tp.s_end) continue;
+        for (int blk = (int)(it % split); blk < nblk; blk += split) {
+            const int xi = tp.x_begin + blk * 32 + lane;
+            if (xi >= tp.x_end) continue;
+            const double dxi = gp.dist[xi];
+            float term = 0.f;
+            if (xi - m >= 0) term += exact_term<NEAR>(gp, ti, xi - m, dxi);
+            if (m != 0 && xi + m < tp.T) term += exact_term<NEAR>(gp, ti, xi + m, dxi);
+            if (term != 0.f) atomicAdd(&tp.out[(size_t)ti * tp.ldo + (xi - tp.x_begin)], term);
+            if (tp.stats) atomicAdd(&tp.stats[1], 1ull);
+        }
     }
 }
 
@@ -566,6 +572,11 @@ struct KirchPipe {
     int nchunks;
     cudaStream_t up, down;
     cudaEvent_t ev_up[KP_MAX_CHUNKS], ev_done[KP_MAX_CHUNKS], ev_entry, ev_exit;
+};
+// Row-range call (impdar_kirchhoff_rows_f32): output rows [s_begin, s_end) only; d/dt rows [g_hi, snum) are already in
+// the workspace from the previous call of the same bottom-up sequence (g_hi == snum: first call, full preparation).
+struct KirchRows {
+    int s_begin, s_end, g_hi;
 };
 static KirchPipe g_pipe;
 static int g_pipe_dev = -1;
@@ -615,7 +626,8 @@ size_t impdar_kirchhoff_workspace_bytes(int S, int T, int nearfield) {
 
 static int kirchhoff_impl(const float *data, float *out, int S, int T, const double *dist_m, const double *tt_s,
                           const double *grad_coef, double vel, int nearfield, int x_begin, int x_end,
-                          void *workspace, size_t ws_bytes, void *stream, const KirchPipe *pipe) {
+                          void *workspace, size_t ws_bytes, void *stream, const KirchPipe *pipe,
+                          const KirchRows *rows = nullptr) {
     IMPDAR_CHECK_ARG(data && out && dist_m && tt_s && grad_coef, "kirchhoff: null pointer");
     IMPDAR_CHECK_ARG(S >= 2 && T >= 1, "kirchhoff: need snum >= 2, tnum >= 1");
     IMPDAR_CHECK_ARG(0 <= x_begin && x_begin < x_end && x_end <= T, "kirchhoff: bad output range [%d, %d)",
@@ -685,7 +697,8 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
     IMPDAR_CUDA(cudaMemcpyAsync(d_tt, tt_s, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
     IMPDAR_CUDA(cudaMemcpyAsync(d_coef, grad_coef, 3 * (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
     IMPDAR_CUDA(cudaMemcpyAsync(d_dist, dist_m, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, st));
-    IMPDAR_CUDA(cudaMemsetAsync(flags, 0, 128, st));
+    const bool continuing = rows && rows->g_hi < S;   // later call of a bottom-up row sequence: flags, tables, d/dt rows stay
+    if (!continuing) IMPDAR_CUDA(cudaMemsetAsync(flags, 0, 128, st));
     kirch_prep_vectors_kernel<<<(S + 255) / 256, 256, 0, st>>>(d_tt, zs, zs2, S, vel);
     IMPDAR_LAUNCH_CHECK();
 
@@ -728,9 +741,9 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
         int *amb_count = flags + 8;
         IMPDAR_CHECK_ARG((unsigned long long)S * (unsigned long long)A1 < (1ull << 31), "kirchhoff: table too large");
         IMPDAR_CHECK_ARG((size_t)(w - (char *)workspace) <= ws_bytes, "kirchhoff: workspace too small for the table path");
-        IMPDAR_CUDA(cudaMemsetAsync(gP, 0, img * (nearfield ? 2 : 1), st));
-        IMPDAR_CUDA(cudaMemsetAsync(nm, 0, (size_t)S * sizeof(int), st));
-        {
+        if (!continuing) {
+            IMPDAR_CUDA(cudaMemsetAsync(gP, 0, img * (nearfield ? 2 : 1), st));
+            IMPDAR_CUDA(cudaMemsetAsync(nm, 0, (size_t)S * sizeof(int), st));
             dim3 grid((A1 + 127) / 128, S);
             kirch_table_build_kernel<<<grid, 128, 0, st>>>(tab, tabn, nm, S, A1, dxm, zs, zs2, d_tt, vel, tmax, tt0,
                                                           1.0 / dt_eff, eps_t, amb_list, amb_count);
@@ -743,10 +756,11 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
         p.gradT = gP; p.dataT = dP; p.rowmajor = 1; p.Tp = Tp; p.Apad = Apad;
         // Row chunks, bottom-up.  Without a host pipeline this is one chunk covering the whole image.
         const int nchunks = pipe ? pipe->nchunks : 1;
-        int g_hi = S;   // d/dt rows [g_hi, S) are built
+        int g_hi = rows ? rows->g_hi : S;   // d/dt rows [g_hi, S) are built
         int u_hi = S;   // input rows [u_hi, S) are uploaded
         for (int j = nchunks - 1; j >= 0; --j) {
-            const int r0 = (int)((long long)S * j / nchunks), r1 = (int)((long long)S * (j + 1) / nchunks);
+            const int r0 = rows ? rows->s_begin : (int)((long long)S * j / nchunks);
+            const int r1 = rows ? rows->s_end : (int)((long long)S * (j + 1) / nchunks);
             if (r1 <= r0) continue;
             if (pipe) {
                 // rows r0 - 1 .. : what the d/dt stencil of rows >= r0 reads
@@ -761,12 +775,14 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
             }
             {
                 const int g0 = r0;   // row r0 - 1 is uploaded (or r0 == 0: one-sided stencil)
-                int gx = (T + 255) / 256;
-                if (gx > 64) gx = 64;
-                dim3 grid(gx, g_hi - g0);
-                grad_padded_kernel<<<grid, 256, 0, st>>>(data, gP, dP, S, T, Tp, Apad, d_coef, flags, g0);
-                IMPDAR_LAUNCH_CHECK();
-                g_hi = g0;
+                if (g0 < g_hi) {
+                    int gx = (T + 255) / 256;
+                    if (gx > 64) gx = 64;
+                    dim3 grid(gx, g_hi - g0);
+                    grad_padded_kernel<<<grid, 256, 0, st>>>(data, gP, dP, S, T, Tp, Apad, d_coef, flags, g0);
+                    IMPDAR_LAUNCH_CHECK();
+                    g_hi = g0;
+                }
             }
             tp.s_begin = r0; tp.s_end = r1;
             dim3 grid(r1 - r0, (x_end - x_begin + 4 * 32 * KT_R - 1) / (4 * 32 * KT_R));
@@ -795,6 +811,7 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
             }
         }
     } else {
+        IMPDAR_CHECK_ARG(!rows, "kirchhoff_rows: row-range calls need uniform trace spacing (the table path)");
         IMPDAR_CHECK_ARG((unsigned long long)(T + 32) * (unsigned long long)kirch_sp(S) < (1ull << 32),
                          "kirchhoff: (tnum + 32) * padded snum must stay below 2^32 elements");
         const int SP = kirch_sp(S);
@@ -842,6 +859,16 @@ int impdar_kirchhoff_f32(const float *data, float *out, int S, int T, const doub
                          void *workspace, size_t ws_bytes, void *stream) {
     return kirchhoff_impl(data, out, S, T, dist_m, tt_s, grad_coef, vel, nearfield, x_begin, x_end, workspace, ws_bytes,
                           stream, nullptr);
+}
+
+int impdar_kirchhoff_rows_f32(const float *data, float *out, int S, int T, const double *dist_m, const double *tt_s,
+                              const double *grad_coef, double vel, int nearfield, int x_begin, int x_end, int s_begin,
+                              int s_end, int g_hi, void *workspace, size_t ws_bytes, void *stream) {
+    IMPDAR_CHECK_ARG(0 <= s_begin && s_begin < s_end && s_end <= S && s_end <= g_hi && g_hi <= S,
+                     "kirchhoff_rows: need 0 <= s_begin < s_end <= g_hi <= snum, got [%d, %d), g_hi %d", s_begin, s_end, g_hi);
+    KirchRows rows = {s_begin, s_end, g_hi};
+    return kirchhoff_impl(data, out, S, T, dist_m, tt_s, grad_coef, vel, nearfield, x_begin, x_end, workspace, ws_bytes,
+                          stream, nullptr, &rows);
 }
 
 size_t impdar_kirchhoff_host_workspace_bytes(int S, int T, int nearfield) {

@@ -98,6 +98,25 @@ def kirchhoff_device(data_dev, travel_time_us, dist_km, vel, nearfield, x_begin=
     return out
 
 
+def kirchhoff_rows_device(data_dev, travel_time_us, dist_km, vel, nearfield, x_begin, x_end, s_begin, s_end, g_hi, out):
+    """Output rows [s_begin, s_end) of the trace range [x_begin, x_end) into the (snum, x_end - x_begin) tensor `out`
+    (impdar_kirchhoff_rows_f32).  Only input rows >= s_begin - 1 of `data_dev` need to be valid.  Calls of one image
+    go bottom-up on the same stream; g_hi = snum for the first, the previous call's s_begin afterwards.  Raises
+    ValueError for irregular trace spacing (use kirchhoff_device)."""
+    lib = _lib.load()
+    S, T = data_dev.shape
+    tt_sec = device.host_f64(travel_time_us) / 1.0e6
+    dist_m = np.ascontiguousarray(device.host_f64(dist_km) * 1.0e3)
+    coef = gradient_coefficients(tt_sec)
+    ws = device.workspace(lib.impdar_kirchhoff_workspace_bytes(S, T, int(bool(nearfield))))
+    rc = lib.impdar_kirchhoff_rows_f32(device.ptr(data_dev), device.ptr(out), S, T, device.ptr(dist_m),
+                                       device.ptr(tt_sec), device.ptr(coef), float(vel), int(bool(nearfield)),
+                                       int(x_begin), int(x_end), int(s_begin), int(s_end), int(g_hi),
+                                       device.ptr(ws), ws.numel(), device.current_stream_ptr())
+    _lib.check(rc)
+    return out
+
+
 def kirchhoff_host(data, travel_time_us, dist_km, vel, nearfield, nchunks=None):
     """Host numpy radargram -> host float64 migrated image with upload, kernels and download overlapped in row
     chunks (impdar_kirchhoff_host_pipelined_f64).  The result lives in page-locked memory owned by the array."""

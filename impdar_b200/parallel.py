@@ -73,26 +73,102 @@ def kirchhoff_output_range(tnum, rank, world, travel_time_us, dist_km, vel):
     return kirchhoff_output_ranges(tnum, world, travel_time_us, dist_km, vel)[rank]
 
 
+def row_chunks(snum, nchunks):
+    """[(r0, r1)] of the bottom-up row pipeline, listed top-down (chunk j = rows [snum j / n, snum (j+1) / n))."""
+    n = max(1, min(int(nchunks), int(snum)))
+    return [(snum * j // n, snum * (j + 1) // n) for j in range(n)]
+
+
+def _kirchhoff_sharded_pipelined(x, travel_time_us, dist_km, vel, nearfield, rank, world, group, src, ranges,
+                                 nchunks, compute_rows):
+    """The exchange steps overlapped with the diffraction sum.  An output row only reads input rows at or below it
+    (minus one for the d/dt stencil), so the input is broadcast bottom-up in row chunks, every chunk of this rank's
+    output range is computed as soon as its rows have arrived, and its all-gather runs while the next chunk is
+    computed.  Returns the assembled (snum, tnum) image, or None when `compute_rows` reports irregular trace spacing
+    on the first chunk (nothing has been computed then; the input is completely broadcast on return)."""
+    import torch
+    import torch.distributed as dist
+    S, T = x.shape
+    xb, xe = ranges[rank]
+    wmax = max(e - b for b, e in ranges)
+    chunks = row_chunks(S, nchunks)
+    # 1. every broadcast is enqueued up front, bottom-up; the collective stream runs them back to back
+    arrive = {}
+    u_hi = S
+    for j in reversed(range(len(chunks))):
+        u0 = max(chunks[j][0] - 1, 0)
+        arrive[j] = dist.broadcast(x[u0:u_hi], src=src, group=group, async_op=True) if u0 < u_hi else None
+        u_hi = min(u_hi, u0)
+    # 2. chunk by chunk: wait for its rows, compute, start its all-gather
+    block = torch.empty((S, max(xe - xb, 0)), dtype=x.dtype, device=x.device)
+    padded = torch.zeros((S, wmax), dtype=x.dtype, device=x.device)
+    stages, gathers = {}, {}
+    g_hi = S
+    for j in reversed(range(len(chunks))):
+        r0, r1 = chunks[j]
+        if arrive[j] is not None:
+            arrive[j].wait()                       # the compute stream waits; the host does not
+        if xe > xb:
+            try:
+                compute_rows(x, travel_time_us, dist_km, vel, nearfield, xb, xe, r0, r1, g_hi, block)
+            except ValueError:
+                if g_hi != S:
+                    raise
+                for w in arrive.values():          # irregular spacing: finish the broadcast, let the caller fall back
+                    if w is not None:
+                        w.wait()
+                return None
+            g_hi = r0
+            padded[r0:r1, :xe - xb] = block[r0:r1]
+        stages[j] = torch.empty((world, r1 - r0, wmax), dtype=x.dtype, device=x.device)
+        gathers[j] = dist.all_gather_into_tensor(stages[j].view(world * (r1 - r0), wmax), padded[r0:r1], group=group,
+                                                 async_op=True)
+    # 3. assemble: (rank, rows, wmax) stages -> column blocks of the image
+    out = torch.empty((S, T), dtype=x.dtype, device=x.device)
+    for j in reversed(range(len(chunks))):
+        r0, r1 = chunks[j]
+        gathers[j].wait()
+        for r, (b, e) in enumerate(ranges):
+            if e > b:
+                out[r0:r1, b:e] = stages[j][r, :, :e - b]
+    return out
+
+
 def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=None, world=None, gather=True,
-                             compute=None, group=None, src=0):
+                             compute=None, group=None, src=0, pipeline_chunks=4, compute_rows=None):
     """Kirchhoff migration of one radargram over all ranks of the process group.
 
     x : (snum, tnum) float32 tensor on this rank's device; only rank `src`'s content matters (it is
         broadcast to the others).  Returns the full (snum, tnum) migrated image on every rank if `gather`,
         else this rank's (snum, x_end - x_begin) block and its range.
     compute(x, travel_time_us, dist_km, vel, nearfield, x_begin, x_end) -> (snum, x_end-x_begin) tensor;
-    defaults to the CUDA kernel (tests on CPU/gloo inject their own)."""
+    defaults to the CUDA kernel (tests on CPU/gloo inject their own).
+    pipeline_chunks > 1 (with `gather`): the broadcast, the kernels and the all-gather overlap in bottom-up row chunks
+    through compute_rows(x, tt, dist, vel, nearfield, x_begin, x_end, s_begin, s_end, g_hi, out) - the CUDA row-range
+    entry by default; irregular trace spacing falls back to the three phases back to back."""
     import torch
     import torch.distributed as dist
+    default_compute = compute is None
     if compute is None:
         from .migrationlib import kirchhoff_device
         compute = kirchhoff_device
+    if compute_rows is None and default_compute:
+        from .migrationlib import kirchhoff_rows_device
+        compute_rows = kirchhoff_rows_device
     if world is None:
         world = dist.get_world_size(group) if dist.is_initialized() else 1
     if rank is None:
         rank = dist.get_rank(group) if dist.is_initialized() else 0
     S, T = x.shape
-    if world > 1:
+    broadcast_done = False
+    if world > 1 and gather and pipeline_chunks > 1 and compute_rows is not None:
+        ranges = kirchhoff_output_ranges(T, world, travel_time_us, dist_km, vel)
+        out = _kirchhoff_sharded_pipelined(x, travel_time_us, dist_km, vel, nearfield, rank, world, group, src, ranges,
+                                           pipeline_chunks, compute_rows)
+        if out is not None:
+            return out
+        broadcast_done = True
+    if world > 1 and not broadcast_done:
         dist.broadcast(x, src=src, group=group)          # the one exchange step on the input side
     ranges = kirchhoff_output_ranges(T, world, travel_time_us, dist_km, vel)
     xb, xe = ranges[rank]

@@ -140,6 +140,17 @@ size_t impdar_kirchhoff_workspace_bytes(int snum, int tnum, int nearfield);
 int impdar_kirchhoff_f32(const float *data, float *out, int snum, int tnum, const double *dist_m,
                          const double *tt_s, const double *grad_coef, double vel, int nearfield,
                          int x_begin, int x_end, void *workspace, size_t workspace_bytes, void *stream);
+/* Row-range form of impdar_kirchhoff_f32 for overlapping the diffraction sum with a collective (the multi-GPU path
+ * broadcasts the input bottom-up in row chunks and gathers finished output rows while the next chunk runs): computes
+ * output rows [s_begin, s_end) of the range [x_begin, x_end) into the full (snum, x_end - x_begin) buffer `out`.  An
+ * output row only reads input rows >= s_begin - 1, so only those need to be valid in `data`.  Calls of one image go
+ * bottom-up on the same workspace and stream: the first passes g_hi = snum (full preparation), every later one passes
+ * the previous call's s_begin (its d/dt rows and the tables are reused).  Uniform trace spacing only (status 1
+ * otherwise: use impdar_kirchhoff_f32).                                                                          */
+int impdar_kirchhoff_rows_f32(const float *data, float *out, int snum, int tnum, const double *dist_m,
+                              const double *tt_s, const double *grad_coef, double vel, int nearfield, int x_begin,
+                              int x_end, int s_begin, int s_end, int g_hi, void *workspace, size_t workspace_bytes,
+                              void *stream);
 /* Host-to-host Kirchhoff with the transfers overlapped (the RadarData.migrate(mtype='kirch') call on a host array):
  * h_data HOST (snum, tnum) floats, h_out HOST (snum, tnum) doubles - page-locked memory makes the copies truly
  * asynchronous.  An output row only reads input rows at or below it (the hyperbola runs downwards in time), so the

@@ -38,6 +38,32 @@ def _worker(rank, world, port, q):
     out = parallel.kirchhoff_sharded_device(x, tt, dk, 1.69e8, False, rank=rank, world=world, compute=compute)
     ref = om.kirchhoff(full.astype(np.float64), tt, dk, 1.69e8, False)
     err = float(np.linalg.norm(out.numpy() - ref) / np.linalg.norm(ref))
+
+    # the pipelined exchange: bottom-up row chunks.  The injected row-range compute poisons every input row the
+    # chunk is not allowed to read (rows < s_begin - 1), so a wrong dependency claim would wreck the result.
+    calls = []
+
+    def compute_rows(xt, tt_, dk_, vel, nf, xb, xe, r0, r1, g_hi, out_block):
+        calls.append((r0, r1, g_hi))
+        src = xt.numpy().astype(np.float64).copy()
+        src[:max(r0 - 1, 0)] = 1e30
+        out_block[r0:r1] = torch.from_numpy(om.kirchhoff(src, tt_, dk_, vel, nf, xb, xe)[r0:r1].astype(np.float32))
+
+    x2 = torch.from_numpy(full.copy()) if rank == 0 else torch.zeros((S, T), dtype=torch.float32)
+    out2 = parallel.kirchhoff_sharded_device(x2, tt, dk, 1.69e8, False, rank=rank, world=world, compute=compute,
+                                             compute_rows=compute_rows, pipeline_chunks=5)
+    err = max(err, float(np.linalg.norm(out2.numpy() - ref) / np.linalg.norm(ref)))
+    assert [c[:2] for c in calls] == list(reversed(parallel.row_chunks(S, 5)))
+    assert [c[2] for c in calls] == [S] + [c[0] for c in calls[:-1]]          # g_hi chains bottom-up
+    assert np.array_equal(x2.numpy(), full)                                  # every rank ends up with the whole input
+
+    def irregular(*a):
+        raise ValueError('kirchhoff_rows: row-range calls need uniform trace spacing (the table path)')
+
+    x3 = torch.from_numpy(full.copy()) if rank == 0 else torch.zeros((S, T), dtype=torch.float32)
+    out3 = parallel.kirchhoff_sharded_device(x3, tt, dk, 1.69e8, False, rank=rank, world=world, compute=compute,
+                                             compute_rows=irregular, pipeline_chunks=4)
+    err = max(err, float(np.linalg.norm(out3.numpy() - ref) / np.linalg.norm(ref)))
     block, rng_ = parallel.kirchhoff_sharded_device(x, tt, dk, 1.69e8, False, rank=rank, world=world,
                                                     compute=compute, gather=False)
     q.put((rank, err, tuple(block.shape), rng_))
