@@ -238,75 +238,105 @@ def _interp1d_vector(x, y, x_new):
 
 
 # ------------------------------------------------------------------------------------------ the methods
+_PER_TRACE = ('lat', 'long', 'pressure', 'trace_int', 'trig', 'elev', 'x_coord', 'y_coord', 'decday')
+
+
+def _picks(self):
+    return getattr(self, 'picks', None)
+
+
+def _set_flag_pair(flags, name, value):
+    """flags.<name> = [1, value]; flag vectors that came back malformed from old .mat files are rebuilt
+    (_RadarDataProcessing.py:182-187, :578-584)."""
+    try:
+        vec = getattr(flags, name)
+        vec[0] = 1
+        vec[1] = value
+    except (IndexError, TypeError):
+        setattr(flags, name, np.array([1., value]))
+
+
+def _note_vertical_crop(self, first, last):
+    """flags.crop = [1, first row kept, one past the last row kept] relative to the original file (:338-349)."""
+    try:
+        base = self.flags.crop[1]
+        self.flags.crop[0] = 1
+        self.flags.crop[2] = base + last
+    except (IndexError, TypeError):
+        self.flags.crop = np.array([1., 0., float(last)])
+    self.flags.crop[1] = self.flags.crop[1] + first
+    print('Vertical samples reduced to subset [{:d}:{:d}] of original'.format(int(self.flags.crop[1]),
+                                                                             int(self.flags.crop[2])))
+
+
 def reverse(self):
     """Flip the profile left-right; mirrors _RadarDataProcessing.py:20-47."""
-    S, T = int(self.data.shape[0]), int(self.data.shape[1])
-    _crop_any(self, 0, S, 0, T, flip_lr=True)
+    nrow, ncol = (int(n) for n in self.data.shape[:2])
+    _crop_any(self, 0, nrow, 0, ncol, flip_lr=True)
     for name in ('x_coord', 'y_coord', 'decday', 'lat', 'long', 'elev'):
-        if getattr(self, name, None) is not None:       # impdar_b200.RadarData leaves absent GPS vectors as None
-            setattr(self, name, np.flip(getattr(self, name), 0))
-    if getattr(self, 'picks', None) is not None:
+        vec = getattr(self, name, None)
+        if vec is not None:       # impdar_b200.RadarData leaves absent GPS vectors as None
+            setattr(self, name, np.flip(vec, 0))
+    if _picks(self) is not None:
         self.picks.reverse()
-    if self.flags.reverse:
-        print('Back to original direction')
-        self.flags.reverse = False
-    else:
-        print('Profile direction reversed')
-        self.flags.reverse = True
+    was_reversed = bool(self.flags.reverse)
+    print('Back to original direction' if was_reversed else 'Profile direction reversed')
+    self.flags.reverse = not was_reversed
 
 
 def constant_sample_depth_spacing(self):
     """Resample rows to constant depth spacing; mirrors _RadarDataProcessing.py:50-63."""
-    if self.nmo_depth is None:
+    old = self.nmo_depth
+    if old is None:
         raise AttributeError('Call nmo first...')
-    if np.allclose(np.diff(self.nmo_depth), np.ones((self.snum - 1,)) * (self.nmo_depth[1] - self.nmo_depth[0])):
+    if np.allclose(np.diff(old), np.ones((self.snum - 1,)) * (old[1] - old[0])):
         print('No constant sampling when you already have constant sampling...')
         return 1
-    depths = np.linspace(np.min(self.nmo_depth[0], 0), self.nmo_depth[-1], len(self.nmo_depth))
+    new = np.linspace(np.min(old[0], 0), old[-1], len(old))
     x, suffix, host_dtype = _stage_float(self.data)
-    nodes = linear_nodes_scipy(self.nmo_depth, depths)
-    so, od = _out_kind(self, suffix, host_dtype)
-    _finish(self, interp_rows_device(x, so, od, nodes, 0), host_dtype)
-    self.travel_time = _interp1d_vector(self.nmo_depth, self.travel_time, depths)
-    self.nmo_depth = depths
+    kernel_suffix, out_dtype = _out_kind(self, suffix, host_dtype)
+    _finish(self, interp_rows_device(x, kernel_suffix, out_dtype, linear_nodes_scipy(old, new), 0), host_dtype)
+    self.travel_time = _interp1d_vector(old, self.travel_time, new)
+    self.nmo_depth = new
 
 
 def traveltime_to_depth(self, profile_depth, profile_rho, c=3.0e8, permittivity_model=firn_permittivity):
     """Depth of every sample for a density profile; mirrors _RadarDataProcessing.py:191-235 (O(snum) host)."""
-    profile_u = c / np.sqrt(np.real(permittivity_model(profile_rho)))
+    speed = c / np.sqrt(np.real(permittivity_model(profile_rho)))
     depth = self.travel_time / 2. * c / np.sqrt(np.real(permittivity_model(917.))) * 1.0e-6
     z = 0.
-    first = self.dt * 1.0e6
-    for i, t in enumerate(self.travel_time):
+    step_us = self.dt * 1.0e6
+    for k, t in enumerate(self.travel_time):
         if t < 0.:
-            continue
-        if t < first:
-            z += t / 2. * profile_u[0] * 1.0e-6
+            continue                                    # pre-trigger samples keep the solid-ice estimate
+        if t < step_us:
+            z += t / 2. * speed[0] * 1.0e-6
         else:
-            z += self.dt / 2. * profile_u[np.nanargmin(abs(profile_depth - z))]
-        depth[i] = z
+            z += self.dt / 2. * speed[np.nanargmin(abs(profile_depth - z))]
+        depth[k] = z
     return depth
 
 
 def _nmo_times(self, ant_sep, uice, u_interp=None, d_interp=None):
-    """Vertical two-way time of every sample (_RadarDataProcessing.py:133-160), float64 host."""
-    tt = self.travel_time
-    nmotime = np.zeros((len(tt)))
-    for i, t in enumerate(tt):
-        if u_interp is None:
-            u_rms = uice
-        else:
-            d = t / 2. * uice * 1.0e-6
-            d_last = d.copy()
-            j, tol = 0, 0.1 * self.dt / 2. * uice
-            while abs(d - d_last) > tol or j < 5:
-                d_last = d.copy()
-                u_rms = np.sqrt(np.mean(u_interp[d_interp <= d] ** 2.))
-                d = t / 2. * u_rms * 1.0e-6
-                j += 1
-        tsep_ice = 1e6 * (ant_sep / u_rms)
-        nmotime[i] = np.sqrt((t + tsep_ice) ** 2. - tsep_ice ** 2.)
-    return nmotime
+    """Vertical two-way time of every sample (_RadarDataProcessing.py:133-160), float64 host.  With a firn profile the
+    RMS velocity above the reflector is iterated to a fixed point exactly like the reference (at least five rounds,
+    np.mean of the squared speeds above the current depth guess)."""
+    out = np.zeros((len(self.travel_time)))
+    tol = 0.1 * self.dt / 2. * uice
+    for k, t in enumerate(self.travel_time):
+        u_rms = uice
+        if u_interp is not None:
+            guess = t / 2. * uice * 1.0e-6
+            previous = guess.copy()
+            rounds = 0
+            while abs(guess - previous) > tol or rounds < 5:
+                previous = guess.copy()
+                u_rms = np.sqrt(np.mean(u_interp[d_interp <= guess] ** 2.))
+                guess = t / 2. * u_rms * 1.0e-6
+                rounds += 1
+        t_sep = 1e6 * (ant_sep / u_rms)                 # direct arrival across the antenna separation [us]
+        out[k] = np.sqrt((t + t_sep) ** 2. - t_sep ** 2.)
+    return out
 
 
 def nmo(self, ant_sep, uice=1.69e8, uair=3.0e8, const_firn_offset=None, rho_profile=None,
@@ -316,20 +346,20 @@ def nmo(self, ant_sep, uice=1.69e8, uair=3.0e8, const_firn_offset=None, rho_prof
     if np.any(self.trig > 0):
         raise ImpdarError('Crop out the pretrigger before doing the nmo correction.')
 
-    u_interp = d_interp = None
+    firn = None
     if rho_profile is not None:
         try:
-            rho_profile_data = np.genfromtxt(rho_profile, delimiter=',')
-            profile_depth = rho_profile_data[:, 0]
-            profile_rho = rho_profile_data[:, 1]
+            table = np.genfromtxt(rho_profile, delimiter=',')
+            firn = (table[:, 0], table[:, 1])
         except IndexError:
             raise IndexError('Cannot load the depth-density profile')
-        profile_u = uair / np.sqrt(np.real(permittivity_model(profile_rho)))
-        d_interp = np.linspace(np.min(profile_depth, 0), max(profile_depth), 10 * self.snum)
-        u_interp = _interp1d_vector(profile_depth, profile_u, d_interp)
+        speed = uair / np.sqrt(np.real(permittivity_model(firn[1])))
+        d_interp = np.linspace(np.min(firn[0], 0), max(firn[0]), 10 * self.snum)
+        u_interp = _interp1d_vector(firn[0], speed, d_interp)
         print('Iterating velocity profile in firn...')
-
-    nmotime = _nmo_times(self, ant_sep, uice, u_interp, d_interp)
+        nmotime = _nmo_times(self, ant_sep, uice, u_interp, d_interp)
+    else:
+        nmotime = _nmo_times(self, ant_sep, uice)
     new_tt = np.arange(min(self.travel_time), max(nmotime), self.dt * 1e6)
 
     x, suffix, host_dtype = _stage_float(self.data)
@@ -338,28 +368,36 @@ def nmo(self, ant_sep, uice=1.69e8, uair=3.0e8, const_firn_offset=None, rho_prof
         nodes, mode = linear_nodes_numpy(nmotime, new_tt), 1
     else:
         nodes, mode = linear_nodes_scipy(nmotime, new_tt), 0
-    so, od = _out_kind(self, suffix, host_dtype)
-    out = interp_rows_device(x, so, od, nodes, mode)
+    kernel_suffix, out_dtype = _out_kind(self, suffix, host_dtype)
+    resampled = interp_rows_device(x, kernel_suffix, out_dtype, nodes, mode)
     self.travel_time = new_tt
     self.snum = len(new_tt)
-    _finish(self, out, host_dtype)
+    _finish(self, resampled, host_dtype)
 
-    if rho_profile is None:
+    if firn is None:
         self.nmo_depth = self.travel_time / 2. * uice * 1.0e-6
     else:
-        self.nmo_depth = traveltime_to_depth(self, profile_depth, profile_rho, c=uair,
-                                             permittivity_model=permittivity_model)
+        self.nmo_depth = traveltime_to_depth(self, firn[0], firn[1], c=uair, permittivity_model=permittivity_model)
     if const_sample:
         constant_sample_depth_spacing(self)
     if const_firn_offset is not None:
         self.nmo_depth = self.nmo_depth + const_firn_offset
     print('Normal Moveout filter complete.')
-    try:
-        self.flags.nmo[0] = 1
-        self.flags.nmo[1] = ant_sep
-    except (IndexError, TypeError):
-        self.flags.nmo = np.ones((2, ))
-        self.flags.nmo[1] = ant_sep
+    _set_flag_pair(self.flags, 'nmo', ant_sep)
+
+
+def _crop_index(self, lim, dimension, uice):
+    """First sample at or beyond `lim` in the chosen unit (_RadarDataProcessing.py:271-288)."""
+    if dimension == 'twtt':
+        return np.min(np.argwhere(self.travel_time >= lim))
+    if dimension == 'depth':
+        depth = getattr(self, 'nmo_depth', None)
+        if depth is None:
+            depth = self.travel_time / 2. * uice * 1.0e-6
+        return np.min(np.argwhere(depth >= lim))
+    if dimension == 'pretrig':
+        return self.trig.astype(int) if isinstance(self.trig, np.ndarray) else int(self.trig)
+    return int(lim)
 
 
 def crop(self, lim, top_or_bottom='top', dimension='snum', uice=1.69e8, rezero=True, zero_trig=True):
@@ -371,66 +409,58 @@ def crop(self, lim, top_or_bottom='top', dimension='snum', uice=1.69e8, rezero=T
     if top_or_bottom == 'bottom' and dimension == 'pretrig':
         raise ValueError('Only use pretrig to crop from the top')
 
-    if dimension == 'twtt':
-        ind = np.min(np.argwhere(self.travel_time >= lim))
-    elif dimension == 'depth':
-        nmo_depth = getattr(self, 'nmo_depth', None)
-        depth = nmo_depth if nmo_depth is not None else self.travel_time / 2. * uice * 1.0e-6
-        ind = np.min(np.argwhere(depth >= lim))
-    elif dimension == 'pretrig':
-        ind = self.trig.astype(int) if isinstance(self.trig, np.ndarray) else int(self.trig)
-    else:
-        ind = int(lim)
-
-    S, T = int(self.data.shape[0]), int(self.data.shape[1])
-    if not isinstance(ind, np.ndarray) or (dimension != 'pretrig'):
+    ind = _crop_index(self, lim, dimension, uice)
+    nrow, ncol = (int(n) for n in self.data.shape[:2])
+    per_trace = isinstance(ind, np.ndarray) and dimension == 'pretrig'
+    if not per_trace:
+        # one limit for the whole profile: a row block
         if top_or_bottom == 'top':
-            lims = [ind, S]
-            self.trig = self.trig - ind
-            if zero_trig:
-                self.trig = np.zeros_like(self.trig)
+            first, last = ind, nrow
+            self.trig = np.zeros_like(self.trig) if zero_trig else self.trig - ind
         else:
-            lims = [0, ind]
-        r0, r1, _ = slice(lims[0], lims[1]).indices(S)       # Python slice semantics (negative / oversize limits)
-        _crop_any(self, r0, max(r0, r1), 0, T)
-        self.travel_time = self.travel_time[lims[0]:lims[1]]
-        if rezero:
-            self.travel_time = self.travel_time - self.travel_time[0]
+            first, last = 0, ind
+        keep = slice(first, last)
+        r0, r1, _ = keep.indices(nrow)                  # Python slice semantics (negative / oversize limits)
+        _crop_any(self, r0, max(r0, r1), 0, ncol)
         if getattr(self, 'nmo_depth', None) is not None:
-            self.nmo_depth = self.nmo_depth[lims[0]:lims[1]]
-        self.snum = self.data.shape[0]
+            self.nmo_depth = self.nmo_depth[keep]
     else:
-        # pretrigger given per trace: shift every trace up by its own trigger sample, NaN below
+        # pretrigger given per trace: every trace moves up by its own trigger sample, NaN below
         ind = np.asarray(ind)
-        if ind.shape != (T,):
+        if ind.shape != (ncol,):
             raise ValueError('trig must have one entry per trace')
-        mintrig = np.nanmin(ind)
-        if mintrig < 0:
+        first, last = np.nanmin(ind), nrow
+        if first < 0:
             raise ValueError('could not broadcast input array: negative trigger samples cannot be cropped')
-        lims = [mintrig, S]
+        keep = slice(first, last)
         self.trig = self.trig - ind
         x, suffix, host_dtype = _stage_float(self.data)
-        so, od = _out_kind(self, suffix, host_dtype)
-        _finish(self, shift_traces_device(x, so, od, ind, S - int(mintrig)), host_dtype)
-        self.travel_time = self.travel_time[lims[0]:lims[1]]
-        if rezero:
-            self.travel_time = self.travel_time - self.travel_time[0]
-        self.snum = self.data.shape[0]
+        kernel_suffix, out_dtype = _out_kind(self, suffix, host_dtype)
+        _finish(self, shift_traces_device(x, kernel_suffix, out_dtype, ind, nrow - int(first)), host_dtype)
+    tt = self.travel_time[keep]
+    self.travel_time = tt - tt[0] if rezero else tt
+    self.snum = self.data.shape[0]
 
-    if top_or_bottom == 'top':
-        if getattr(self, 'picks', None) is not None:
-            self.picks.crop(ind)
+    if top_or_bottom == 'top' and _picks(self) is not None:
+        self.picks.crop(ind)
+    _note_vertical_crop(self, first, last)
 
-    try:
-        self.flags.crop[0] = 1
-        self.flags.crop[2] = self.flags.crop[1] + lims[1]
-    except (IndexError, TypeError):
-        self.flags.crop = np.zeros((3,))
-        self.flags.crop[0] = 1
-        self.flags.crop[2] = self.flags.crop[1] + lims[1]
-    self.flags.crop[1] = self.flags.crop[1] + lims[0]
-    print('Vertical samples reduced to subset [{:d}:{:d}] of original'.format(
-        int(self.flags.crop[1]), int(self.flags.crop[2])))
+
+def _hcrop_index(self, lim, dimension):
+    """Zero-based trace index of the crop limit with the reference's validity rules (:377-392)."""
+    if dimension == 'dist':
+        if lim > np.max(self.dist):
+            raise ValueError('lim is larger than largest distance')
+        if lim <= 0:
+            raise ValueError('Distance should be strictly positive')
+        return np.min(np.argwhere(self.dist >= lim))
+    if int(lim) in (0, 1):
+        raise ValueError('lim should be at least two to preserve some data')
+    if lim > self.tnum:
+        raise ValueError('lim should be less than tnum+1 {:d} in order to do anything'.format(self.tnum + 1))
+    if lim == -1 or lim < -int(self.tnum):
+        raise ValueError('If negative, lim should be in [-self.tnum; -1)')
+    return int(lim) - 1                                 # trace numbers are 1-indexed
 
 
 def hcrop(self, lim, left_or_right='left', dimension='tnum'):
@@ -439,36 +469,22 @@ def hcrop(self, lim, left_or_right='left', dimension='tnum'):
         raise ValueError('left_or_right must be left or right, not {:s}'.format(left_or_right))
     if dimension not in ['tnum', 'dist']:
         raise ValueError('Dimension must be in ["tnum", "dist"]')
-
-    if dimension == 'dist':
-        if lim > np.max(self.dist):
-            raise ValueError('lim is larger than largest distance')
-        if lim <= 0:
-            raise ValueError('Distance should be strictly positive')
-        ind = np.min(np.argwhere(self.dist >= lim))
-    else:
-        if int(lim) in (0, 1):
-            raise ValueError('lim should be at least two to preserve some data')
-        if lim > self.tnum:
-            raise ValueError('lim should be less than tnum+1 {:d} in order to do anything'.format(self.tnum + 1))
-        if lim == -1 or lim < -int(self.tnum):
-            raise ValueError('If negative, lim should be in [-self.tnum; -1)')
-        ind = int(lim) - 1
-
-    S, T = int(self.data.shape[0]), int(self.data.shape[1])
-    lims = [ind, T] if left_or_right == 'left' else [0, ind]
-    c0, c1, _ = slice(lims[0], lims[1]).indices(T)
-    _crop_any(self, 0, S, c0, max(c0, c1))
-    for var in ['lat', 'long', 'pressure', 'trace_int', 'trig', 'elev', 'x_coord', 'y_coord', 'decday']:
-        val = getattr(self, var, None)
-        if val is not None and isinstance(val, np.ndarray):
-            setattr(self, var, val[lims[0]:lims[1]])
-    if getattr(self, 'picks', None) is not None:
-        self.picks.hcrop(lims)
+    ind = _hcrop_index(self, lim, dimension)
+    nrow, ncol = (int(n) for n in self.data.shape[:2])
+    first, last = (ind, ncol) if left_or_right == 'left' else (0, ind)
+    keep = slice(first, last)
+    c0, c1, _ = keep.indices(ncol)
+    _crop_any(self, 0, nrow, c0, max(c0, c1))
+    for name in _PER_TRACE:                             # scalars (a float trig, a scalar trace_int) stay as they are
+        vec = getattr(self, name, None)
+        if isinstance(vec, np.ndarray):
+            setattr(self, name, vec[keep])
+    if _picks(self) is not None:
+        self.picks.hcrop([first, last])
     if self.dist is not None:
-        self.dist = self.dist[lims[0]:lims[1]] - self.dist[lims[0]]
+        self.dist = self.dist[keep] - self.dist[first]
     if getattr(self, 'trace_num', None) is not None:
-        self.trace_num = self.trace_num[lims[0]:lims[1]] - lims[0] + 1
+        self.trace_num = self.trace_num[keep] - first + 1
     self.tnum = self.data.shape[1]
 
 
@@ -481,110 +497,97 @@ def restack(self, traces):
     if traces % 2 == 0:
         print('Only will stack odd numbers of traces. Using {:d}'.format(int(traces + 1)))
         traces = traces + 1
-    tnum = int(np.floor(self.tnum / traces))
+    groups = int(np.floor(self.tnum / traces))
     x, suffix, host_dtype = _stage_float(self.data)
-    so, od = _out_kind(self, suffix, host_dtype)
-    out = restack_device(x, so, od, traces)
+    kernel_suffix, out_dtype = _out_kind(self, suffix, host_dtype)
+    stacked = restack_device(x, kernel_suffix, out_dtype, traces)
 
-    new_vectors = {}
-    for key in _RESTACK_VARS:
-        val = getattr(self, key, None)
-        if val is None:
-            new_vectors[key] = None
-            continue
-        grouped = np.zeros((tnum, ))
-        for j in range(tnum):
-            grouped[j] = np.mean(val[j * traces:min((j + 1) * traces, int(x.shape[1]))])
-        new_vectors[key] = grouped
-    self.tnum = tnum
-    _finish(self, out, host_dtype)
-    self.trace_num = np.arange(self.tnum).astype(int) + 1
-    self.trace_int = np.zeros((tnum, ))
-    if getattr(self, 'picks', None) is not None:
+    width = int(x.shape[1])
+    averaged = {}
+    for name in _RESTACK_VARS:
+        vec = getattr(self, name, None)
+        averaged[name] = None if vec is None else np.array(
+            [np.mean(vec[g * traces:min((g + 1) * traces, width)]) for g in range(groups)], dtype=np.float64).reshape(groups)
+    self.tnum = groups
+    _finish(self, stacked, host_dtype)
+    self.trace_num = np.arange(groups).astype(int) + 1
+    self.trace_int = np.zeros((groups, ))                # the reference leaves the restacked spacing at zero (:452, :468)
+    if _picks(self) is not None:
         self.picks.restack(traces)
-    for key, val in new_vectors.items():
-        setattr(self, key, val)
+    for name, vec in averaged.items():
+        setattr(self, name, vec)
     self.flags.restack = True
 
 
 def constant_space(self, spacing, min_movement=1.0e-2, show_nomove=False):
     """Resample to constant trace spacing; mirrors _RadarDataProcessing.py:499-584: stationary traces are dropped
     (column compaction) and the rest interpolated linearly in distance - one column-gather pass on the device."""
-    good_vals = np.hstack((np.array([True]), np.diff(self.dist * 1000.) >= min_movement))
-    for i in range(len(self.dist)):
-        if not good_vals[i]:
-            self.dist[i:] = self.dist[i:] - (self.dist[i] - self.dist[i - 1])
-    temp_dist = self.dist[good_vals]
-    new_dists = np.arange(np.min(temp_dist), np.max(temp_dist), step=spacing / 1000.0)
+    moving = np.hstack((np.array([True]), np.diff(self.dist * 1000.) >= min_movement))
+    for k in np.flatnonzero(~moving):                   # close the gaps the dropped traces leave in the distance axis
+        self.dist[k:] = self.dist[k:] - (self.dist[k] - self.dist[k - 1])
+    old = self.dist[moving]
+    new = np.arange(np.min(old), np.max(old), step=spacing / 1000.0)
 
-    nodes = linear_nodes_scipy(temp_dist, new_dists)
-    kept = np.flatnonzero(good_vals)
+    nodes = linear_nodes_scipy(old, new)
+    kept = np.flatnonzero(moving)
     nodes['lo'], nodes['hi'] = kept[nodes['lo']], kept[nodes['hi']]      # compaction folded into the gather
 
-    is_complex = (not device.is_device_array(self.data)) and np.iscomplexobj(np.asarray(self.data))
-    if is_complex:
+    if (not device.is_device_array(self.data)) and np.iscomplexobj(np.asarray(self.data)):
         # real weights times complex samples act on the two components separately: run the float64 kernel on the
         # interleaved (snum, 2 tnum) view with every node duplicated for the real and the imaginary column
+        import torch
         z = np.ascontiguousarray(np.asarray(self.data), dtype=np.complex128)
         both = np.repeat(nodes, 2)
-        both['lo'] = 2 * both['lo'] + np.tile([0, 1], len(nodes))
-        both['hi'] = 2 * both['hi'] + np.tile([0, 1], len(nodes))
-        import torch
+        part = np.tile([0, 1], len(nodes))
+        both['lo'], both['hi'] = 2 * both['lo'] + part, 2 * both['hi'] + part
         x = device.to_device(z.view(np.float64), torch.float64)
-        out = interp_cols_device(x, 'f64', torch.float64, both, 0)
-        self.data = device.to_host(out, np.float64).view(np.complex128)
+        self.data = device.to_host(interp_cols_device(x, 'f64', torch.float64, both, 0), np.float64).view(np.complex128)
     else:
         x, suffix, host_dtype = _stage_float(self.data)
-        so, od = _out_kind(self, suffix, host_dtype)
-        _finish(self, interp_cols_device(x, so, od, nodes, 0), host_dtype)
+        kernel_suffix, out_dtype = _out_kind(self, suffix, host_dtype)
+        _finish(self, interp_cols_device(x, kernel_suffix, out_dtype, nodes, 0), host_dtype)
 
-    for attr in ['lat', 'long', 'x_coord', 'y_coord', 'decday', 'pressure', 'trig']:
-        setattr(self, attr, _interp1d_vector(temp_dist, getattr(self, attr)[good_vals], new_dists))
-    for attr in ['elev']:
-        if getattr(self, attr) is not None:
-            setattr(self, attr, _interp1d_vector(temp_dist, getattr(self, attr)[good_vals], new_dists))
+    def onto_new(values):
+        return _interp1d_vector(old, values, new)
 
-    picks = getattr(self, 'picks', None)
+    for name in ('lat', 'long', 'x_coord', 'y_coord', 'decday', 'pressure', 'trig', 'elev'):
+        vec = getattr(self, name)
+        if name == 'elev' and vec is None:              # elev is the one optional vector (:562-566)
+            continue
+        setattr(self, name, onto_new(vec[moving]))
+    picks = _picks(self)
     if picks is not None:
-        for attr in ['samp1', 'samp2', 'samp3']:
-            if getattr(picks, attr) is not None:
-                setattr(picks, attr, np.round(_interp1d_vector(temp_dist, getattr(picks, attr)[:, good_vals],
-                                                               new_dists)))
-        for attr in ['power', 'time']:
-            if getattr(picks, attr) is not None:
-                setattr(picks, attr, _interp1d_vector(temp_dist, getattr(picks, attr)[:, good_vals], new_dists))
+        for name, rounded in (('samp1', True), ('samp2', True), ('samp3', True), ('power', False), ('time', False)):
+            grid = getattr(picks, name)
+            if grid is not None:
+                grid = onto_new(grid[:, moving])
+                setattr(picks, name, np.round(grid) if rounded else grid)
 
     self.tnum = self.data.shape[1]
     self.trace_num = np.arange(self.tnum).astype(int) + 1
-    self.dist = new_dists
-    self.trace_int = np.hstack((np.array(np.nanmean(np.diff(self.dist))), np.diff(self.dist))) * 1000.
-    try:
-        self.flags.interp[0] = 1
-        self.flags.interp[1] = spacing
-    except (IndexError, TypeError):
-        self.flags.interp = np.ones((2,))
-        self.flags.interp[1] = spacing
+    self.dist = new
+    self.trace_int = np.hstack((np.array(np.nanmean(np.diff(new))), np.diff(new))) * 1000.
+    _set_flag_pair(self.flags, 'interp', spacing)
 
 
 def elev_correct(self, v_avg=1.69e8):
     """Shift every trace down by its surface elevation difference; mirrors _RadarDataProcessing.py:587-637."""
     if getattr(self, 'nmo_depth', None) is None:
         raise ValueError('Run nmo before elev_correct so that we have depth scale')
-    elev_diffs = np.max(self.elev) - self.elev
-    max_diff = np.max(elev_diffs)
-    dz_avg = self.dt * (v_avg / 2.)
-    max_samp = int(np.floor(max_diff / dz_avg))
-    top_inds = (elev_diffs / dz_avg).astype(int)
+    top, bottom = np.max(self.elev), np.min(self.elev)
+    below_top = top - self.elev                          # how far every trace's surface sits below the highest one
+    dz = self.dt * (v_avg / 2.)
+    extra_rows = int(np.floor(np.max(below_top) / dz))
+    shift = (below_top / dz).astype(int)
 
     x, suffix, host_dtype = _stage_float(self.data)
-    so, od = _out_kind(self, suffix, host_dtype)
-    S = int(x.shape[0])
-    if np.any(top_inds + S > S + max_samp) or np.any(top_inds < 0):
+    kernel_suffix, out_dtype = _out_kind(self, suffix, host_dtype)
+    nrow = int(x.shape[0])
+    if np.any(shift > extra_rows) or np.any(shift < 0):
         raise ValueError('could not broadcast input array: a trace would be shifted outside the padded radargram')
-    _finish(self, shift_traces_device(x, so, od, -top_inds, S + max_samp), host_dtype)
+    _finish(self, shift_traces_device(x, kernel_suffix, out_dtype, -shift, nrow + extra_rows), host_dtype)
 
-    if getattr(self, 'picks', None) is not None:
-        self.picks.crop(-top_inds - 1)
-    self.elevation = np.hstack((np.arange(np.max(self.elev), np.min(self.elev), -dz_avg),
-                                np.min(self.elev) - self.nmo_depth))
+    if _picks(self) is not None:
+        self.picks.crop(-shift - 1)
+    self.elevation = np.hstack((np.arange(top, bottom, -dz), bottom - self.nmo_depth))
     self.flags.elev = 1
