@@ -8,6 +8,7 @@ or, without ImpDAR installed, ``impdar_b200.RadarData`` offers the same hot-path
 """
 from . import migrationlib, filtering, processing, process  # noqa: F401  (process.process mirrors impdar.lib.process.process)
 from .radardata import RadarData, RadarFlags  # noqa: F401
+from .matio import load_mat  # noqa: F401  (StoDeep / ImpDAR .mat files)
 from .migrationlib import (migrationKirchhoff, migrationStolt, migrationPhaseShift,  # noqa: F401
                            migrationTimeWavenumber, getVelocityProfile)
 

@@ -26,6 +26,28 @@ class RadarFlags(object):
         self.mig = 'none'
         self.elev = 0
         self.elevation = 0
+        self.attrs = ['batch', 'bpass', 'hfilt', 'rgain', 'agc', 'restack', 'reverse', 'crop', 'nmo', 'interp', 'mig',
+                      'elev']
+        self.attr_dims = [None, 3, 2, None, None, None, None, 3, 2, 2, None, None]
+        self.bool_attrs = ['agc', 'batch', 'restack', 'reverse', 'rgain']
+
+    def to_matlab(self):
+        """dict for scipy.io.savemat; booleans as 0 / 1 (RadarFlags.py:63-75)."""
+        out = {name: getattr(self, name) for name in self.attrs}
+        for name in self.bool_attrs:
+            out[name] = 1 if out[name] else 0
+        return out
+
+    def from_matlab(self, matlab_struct):
+        """Fill from the `flags` struct of scipy.io.loadmat (RadarFlags.py:77-104): vector flags that MATLAB stored as a
+        lazily appended scalar are re-allocated at their proper length."""
+        for name, dim in zip(self.attrs, self.attr_dims):
+            val = matlab_struct[name][0][0][0]
+            if dim is not None and val.shape[0] == 1:
+                val = np.zeros((dim, ))
+            setattr(self, name, val)
+        for name in self.bool_attrs:
+            setattr(self, name, True if matlab_struct[name][0][0][0] == 1 else 0)
 
 
 class RadarData(object):
@@ -49,6 +71,16 @@ class RadarData(object):
         self.nmo_depth = None
         self.elevation = None
         self.picks = None
+        # file-format attributes (RadarData/__init__.py:38-61); filled by impdar_b200.load_mat
+        self.chan = None
+        self.trig_level = None
+        self.t_srs = None
+        self.data_dtype = None if data is None else np.asarray(data).dtype if not hasattr(data, 'is_cuda') else None
+
+    def save(self, fn):
+        """Write a StoDeep / ImpDAR .mat file (RadarData/_RadarDataSaving.py:32-78)."""
+        from . import matio
+        return matio.save(self, fn)
 
     adaptivehfilt = filtering.adaptivehfilt
     horizontalfilt = filtering.horizontalfilt
