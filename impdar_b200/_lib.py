@@ -74,6 +74,8 @@ PROTOTYPES = {
                                  _vp, _c_sz, _vp]),
     "impdar_wiener_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_dbl, _vp, _vp]),
     "impdar_wiener_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_dbl, _vp, _vp]),
+    "impdar_median_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "impdar_median_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
     "impdar_interp_node_bytes": (_c_sz, []),
     "impdar_crop_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
     "impdar_crop_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),

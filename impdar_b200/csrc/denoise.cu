@@ -94,6 +94,64 @@ static int wiener_impl(const T *x, double *y, int S, int Tn, int V, int H, int e
     return IMPDAR_B200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- median filter
+// denoise(ftype='median') = scipy.ndimage.median_filter(data, size=(V, H)) (mode 'reflect', origin 0): the element of
+// rank (V*H)//2 of the window rows [s - V/2, s - V/2 + V), columns [t - H/2, t - H/2 + H), indices reflected about the
+// edges with the edge sample repeated (d c b a | a b c d | d c b a).  Pure selection - bit-exact.  The window is copied
+// once into the thread's local array and the wanted rank is found by counting (n^2 / 2 comparisons, no data movement).
+constexpr int MEDIAN_MAX_WINDOW = 256;
+
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    const int period = 2 * n;
+    i %= period;
+    if (i < 0) i += period;
+    return i < n ? i : period - 1 - i;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) median_kernel(const T *__restrict__ x, T *__restrict__ y, int S, int Tn, int V, int H) {
+    T win[MEDIAN_MAX_WINDOW];
+    const int n = V * H, want = n / 2;
+    for (int s = blockIdx.y; s < S; s += gridDim.y)
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < Tn; t += gridDim.x * blockDim.x) {
+            int k = 0;
+            for (int dv = 0; dv < V; ++dv) {
+                const T *row = x + (size_t)reflect_index(s - V / 2 + dv, S) * Tn;
+                for (int dh = 0; dh < H; ++dh) win[k++] = row[reflect_index(t - H / 2 + dh, Tn)];
+            }
+            T out = win[0];
+            for (int i = 0; i < n; ++i) {
+                const T v = win[i];
+                int less = 0, equal_before = 0;
+                for (int j = 0; j < n; ++j) {
+                    less += (win[j] < v);
+                    equal_before += (j < i) & (win[j] == v);
+                }
+                if (less + equal_before == want) {      // stable rank of element i
+                    out = v;
+                    break;
+                }
+            }
+            y[(size_t)s * Tn + t] = out;
+        }
+}
+
+template <typename T>
+static int median_impl(const T *x, T *y, int S, int Tn, int V, int H, void *stream) {
+    IMPDAR_CHECK_ARG(x && y, "median: null pointer");
+    IMPDAR_CHECK_ARG(S >= 1 && Tn >= 1 && V >= 1 && H >= 1, "median: bad shape or window");
+    IMPDAR_CHECK_ARG((long long)V * H <= MEDIAN_MAX_WINDOW, "median: window of %d x %d samples exceeds the %d supported", V, H,
+                     MEDIAN_MAX_WINDOW);
+    IMPDAR_CHECK_ARG((const void *)x != (const void *)y, "median: in-place not supported");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)min((Tn + 127) / 128, 64), (unsigned)min(S, 16 * num_sms()));
+    ktimer_begin("median_kernel", st);
+    median_kernel<T><<<grid, 128, 0, st>>>(x, y, S, Tn, V, H);
+    ktimer_end(st);
+    IMPDAR_LAUNCH_CHECK();
+    return IMPDAR_B200_OK;
+}
+
 }  // namespace impdar
 
 using namespace impdar;
@@ -107,6 +165,13 @@ int impdar_wiener_f32(const float *x, double *y, int snum, int tnum, int vert_wi
 int impdar_wiener_f64(const double *x, double *y, int snum, int tnum, int vert_win, int hor_win, int estimate_noise,
                       double noise, double *scratch, void *stream) {
     return wiener_impl<double>(x, y, snum, tnum, vert_win, hor_win, estimate_noise, noise, scratch, stream);
+}
+
+int impdar_median_f32(const float *x, float *y, int snum, int tnum, int vert_win, int hor_win, void *stream) {
+    return median_impl<float>(x, y, snum, tnum, vert_win, hor_win, stream);
+}
+int impdar_median_f64(const double *x, double *y, int snum, int tnum, int vert_win, int hor_win, void *stream) {
+    return median_impl<double>(x, y, snum, tnum, vert_win, hor_win, stream);
 }
 
 }  // extern "C"

@@ -449,8 +449,16 @@ def denoise(self, vert_win=1, hor_win=10, noise=None, ftype='wiener'):
         else:
             self.data = device.to_host(out, np.float64)
     elif ftype == 'median':
-        raise NotImplementedError('the median denoising filter (scipy.ndimage.median_filter) is outside the B200 hot '
-                                  'path - use the reference for ftype=median')
+        # scipy.ndimage.median_filter(data, size=(vert_win, hor_win)): pure selection, the dtype is kept
+        import torch
+        x, suffix, np_dtype, was_device = _stage(self.data)
+        if x.dim() != 2:
+            raise ValueError('denoise expects a (snum, tnum) radargram')
+        out = torch.empty_like(x)
+        fn = getattr(_lib.load(), 'impdar_median_' + suffix)
+        _lib.check(fn(device.ptr(x), device.ptr(out), int(x.shape[0]), int(x.shape[1]), int(vert_win), int(hor_win),
+                      device.current_stream_ptr()))
+        _unstage(self, out, np_dtype, was_device)
     else:
         raise ValueError('Only the wiener filter has been implemented for denoising.')
 

@@ -282,6 +282,11 @@ int impdar_wiener_f32(const float *x, double *y, int snum, int tnum, int vert_wi
                       double noise, double *scratch, void *stream);
 int impdar_wiener_f64(const double *x, double *y, int snum, int tnum, int vert_win, int hor_win, int estimate_noise,
                       double noise, double *scratch, void *stream);
+/* denoise(ftype='median') = scipy.ndimage.median_filter(x, size=(vert_win, hor_win)) (mode 'reflect'): rank
+ * (vert_win*hor_win)/2 of the window rows [s - V/2, s - V/2 + V), columns likewise; bit-exact selection.  Windows of up
+ * to 256 samples; y != x.  NaN ordering is unspecified (as in scipy).                                              */
+int impdar_median_f32(const float *x, float *y, int snum, int tnum, int vert_win, int hor_win, void *stream);
+int impdar_median_f64(const double *x, double *y, int snum, int tnum, int vert_win, int hor_win, void *stream);
 
 #ifdef __cplusplus
 }

@@ -304,3 +304,16 @@ def wiener(data, vert_win=1, hor_win=10, noise=None):
         res = res * (1 - noise / var)
         res = res + mean
     return np.where(var < noise, mean, res)
+
+
+def median_filter(data, vert_win=1, hor_win=10):
+    """denoise(ftype='median') (_RadarDataFiltering.py:583-584) = scipy.ndimage.median_filter(data, size=(V, H)): rank
+    (V*H)//2 of the window rows [s - V//2, s - V//2 + V), columns likewise, edges reflected with the edge sample
+    repeated (numpy's 'symmetric' padding); the dtype is kept."""
+    from numpy.lib.stride_tricks import sliding_window_view
+    x = np.asarray(data)
+    S, T = x.shape
+    V, H = int(vert_win), int(hor_win)
+    padded = np.pad(x, ((V // 2, V - 1 - V // 2), (H // 2, H - 1 - H // 2)), mode='symmetric')
+    windows = sliding_window_view(padded, (V, H)).reshape(S, T, V * H)
+    return np.sort(windows, axis=2)[:, :, (V * H) // 2]

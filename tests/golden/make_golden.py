@@ -147,6 +147,15 @@ def run_denoise(tag, data, **mk):
         quiet(d.denoise, **kw)
         save("%s_denoise_%s" % (tag, name), data=x, out=d.data, vert_win=kw.get("vert_win", 1),
              hor_win=kw.get("hor_win", 10), noise=kw.get("noise", np.nan), **geom(d))
+    # ftype='median' (scipy.ndimage.median_filter): default window, odd and even 2-D windows, float32 and int16 data
+    for name, conv, kw in (("v1h10", lambda a: a, {}), ("v3h3", lambda a: a, dict(vert_win=3, hor_win=3)),
+                           ("v4h5_f32", lambda a: a.astype(np.float32), dict(vert_win=4, hor_win=5)),
+                           ("v5h2_i16", lambda a: np.round(a * 100).astype(np.int16), dict(vert_win=5, hor_win=2))):
+        d = make_dat(conv(data), **mk)
+        x = d.data.copy()
+        quiet(d.denoise, ftype='median', **kw)
+        save("%s_median_%s" % (tag, name), data=x, out=d.data, vert_win=kw.get("vert_win", 1),
+             hor_win=kw.get("hor_win", 10), **geom(d))
 
 
 def run_lateral():

@@ -375,3 +375,27 @@ def test_denoise_large_vs_oracle_and_errors():
         d.denoise(vert_win=1, hor_win=3)
     with pytest.raises(ValueError):
         d.denoise(ftype='dummy')
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_median_"))
+def test_denoise_median_golden(name):
+    """Pure selection: bit-exact, dtype kept (float64, float32, int16)."""
+    g = load_golden(name)
+    d = dat_from_golden(g)
+    d.denoise(vert_win=int(g["vert_win"]), hor_win=int(g["hor_win"]), ftype='median')
+    assert d.data.dtype == g["out"].dtype and np.array_equal(d.data, g["out"])
+
+
+def test_denoise_median_large_vs_oracle():
+    from oracle import filtering as of
+    d = synthetic_dat(257, 1031, seed=51)
+    d.data = np.round(d.data * 4) / 4                      # many ties: the stable rank must still pick the right value
+    want = of.median_filter(d.data, 7, 9)
+    d.denoise(vert_win=7, hor_win=9, ftype='median')
+    assert np.array_equal(d.data, want)
+    d = synthetic_dat(5, 6, seed=52)                       # window wider than the radargram: repeated reflection
+    want = of.median_filter(d.data, 3, 15)
+    d.denoise(vert_win=3, hor_win=15, ftype='median')
+    assert np.array_equal(d.data, want)
+    with pytest.raises(ValueError):
+        d.denoise(vert_win=17, hor_win=16, ftype='median')  # 272 samples > the 256 the kernel holds

@@ -138,3 +138,10 @@ def test_denoise_wiener(name):
 def test_denoise_zero_variance_raises_like_reference():
     with pytest.raises(ValueError):
         of.wiener(np.pad(np.ones((4, 40)), ((0, 4), (0, 0))) + np.arange(8)[:, None] * np.r_[np.zeros(20), np.ones(20)], 1, 3)
+
+
+@pytest.mark.parametrize("name", golden_names(contains="_median_"))
+def test_denoise_median(name):
+    g = load_golden(name)
+    out = of.median_filter(g["data"], int(g["vert_win"]), int(g["hor_win"]))
+    assert out.dtype == g["out"].dtype == g["data"].dtype and np.array_equal(out, g["out"])
