@@ -346,3 +346,74 @@ def test_gpu_constant_space_complex():
     want = op.interp_cols_scipy(z, dist, new)
     assert d.data.dtype == np.complex128 and d.data.shape == want.shape
     assert np.array_equal(d.data, want)
+
+
+# ------------------------------------------------ node tables against the real scipy / numpy on random cases (CPU)
+@pytest.mark.parametrize('seed', range(8))
+def test_node_tables_reproduce_scipy_and_numpy_interp(seed):
+    """The host-built node tables, evaluated with the kernels' formulas, equal scipy.interpolate.interp1d (2-D and
+    float32 y: two-weight form) and numpy.interp (1-D float64 y: slope form, exact hits, NaN retry) bit for bit on
+    random abscissae - including repeated query points, exact node hits, both range ends and NaNs in y."""
+    from scipy.interpolate import interp1d
+    rng = np.random.default_rng(100 + seed)
+    n, m, T = int(rng.integers(2, 60)), int(rng.integers(1, 90)), 7
+    x = np.cumsum(rng.random(n) + 1e-3) * (10.0 ** rng.integers(-6, 4))
+    q = rng.uniform(x[0], x[-1], m)
+    q[rng.integers(0, m, min(m, 5))] = x[rng.integers(0, n, min(m, 5))]          # exact node hits
+    q[0], q[-1] = (x[0], x[-1]) if m > 1 else (x[-1], x[-1])
+    q = np.sort(q) if seed % 2 else q
+    Y = rng.standard_normal((n, T))
+    if seed % 3 == 0:
+        Y[rng.integers(0, n), rng.integers(0, T)] = np.nan
+    nodes = processing.linear_nodes_scipy(x, q)
+    got = _emulate_interp(nodes, Y[nodes['lo']], Y[nodes['hi']], 0, 0)
+    assert np.array_equal(got, interp1d(x, Y.T)(q).T, equal_nan=True)
+    Y32 = Y.astype(np.float32)
+    got32 = _emulate_interp(nodes, Y32[nodes['lo']], Y32[nodes['hi']], 0, 0)
+    want32 = np.stack([interp1d(x, Y32[:, t])(q) for t in range(T)], axis=1)          # 1-D float32 y: still scipy's own form
+    assert got32.dtype == np.float64 and np.array_equal(got32, want32, equal_nan=True)
+    nodes = processing.linear_nodes_numpy(x, q)
+    got = _emulate_interp(nodes, Y[nodes['lo']], Y[nodes['hi']], 1, 0)
+    want = np.stack([interp1d(x, Y[:, t])(q) for t in range(T)], axis=1)               # 1-D float64 y: numpy.interp
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.array_equal(want, np.stack([np.interp(q, x, Y[:, t]) for t in range(T)], axis=1), equal_nan=True)
+    with pytest.raises(ValueError):
+        processing.linear_nodes_scipy(x, np.array([x[0] - 1.0]))
+    with pytest.raises(ValueError):
+        processing.linear_nodes_numpy(x, np.array([x[-1] * (1 + 1e-9) + 1e-30]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('seed', range(6))
+def test_gpu_interp_kernels_reproduce_scipy_and_numpy(seed):
+    """The same random cases through the CUDA kernels (rows and columns, both arithmetic forms, float64 and float32
+    input): bit-exact against scipy.interpolate.interp1d / numpy.interp themselves."""
+    import torch
+    from scipy.interpolate import interp1d
+    rng = np.random.default_rng(200 + seed)
+    n, m, T = int(rng.integers(2, 300)), int(rng.integers(1, 400)), int(rng.integers(1, 700))
+    x = np.cumsum(rng.random(n) + 1e-3) * (10.0 ** rng.integers(-6, 4))
+    q = rng.uniform(x[0], x[-1], m)
+    q[rng.integers(0, m, min(m, 5))] = x[rng.integers(0, n, min(m, 5))]
+    q[0] = x[0]
+    q[-1] = x[-1]
+    Y = rng.standard_normal((n, T))
+    if seed % 2 == 0:
+        Y[rng.integers(0, n), rng.integers(0, T)] = np.nan
+    Yd, Yd32 = torch.from_numpy(Y).cuda(), torch.from_numpy(Y.astype(np.float32)).cuda()
+    ns, nn = processing.linear_nodes_scipy(x, q), processing.linear_nodes_numpy(x, q)
+    want = interp1d(x, Y.T)(q).T
+    got = processing.interp_rows_device(Yd, 'f64', torch.float64, ns, 0).cpu().numpy()
+    assert np.array_equal(got, want, equal_nan=True)
+    want32 = interp1d(x, Y.astype(np.float32).T)(q).T
+    got32 = processing.interp_rows_device(Yd32, 'f32_f64', torch.float64, ns, 0).cpu().numpy()
+    assert np.array_equal(got32, want32, equal_nan=True)
+    want_np = np.stack([np.interp(q, x, Y[:, t]) for t in range(T)], axis=1)
+    got_np = processing.interp_rows_device(Yd, 'f64', torch.float64, nn, 1).cpu().numpy()
+    assert np.array_equal(got_np, want_np, equal_nan=True)
+    # columns: the transposed problem
+    Yt = Yd.t().contiguous()
+    got_c = processing.interp_cols_device(Yt, 'f64', torch.float64, ns, 0).cpu().numpy()
+    assert np.array_equal(got_c, want.T, equal_nan=True)
+    got_c32 = processing.interp_cols_device(Yd32.t().contiguous(), 'f32_f64', torch.float64, ns, 0).cpu().numpy()
+    assert np.array_equal(got_c32, want32.T, equal_nan=True)
