@@ -20,7 +20,7 @@ _FILTER_NAMES = ('vertical_band_pass', 'horizontalfilt', 'adaptivehfilt',
                  'highpass', 'lowpass', 'horizontal_band_pass', 'winavg_hfilt', 'rangegain', 'agc', 'denoise')
 # index / resampling operations either side of the path, bound from impdar_b200.processing
 _PROCESSING_NAMES = ('reverse', 'crop', 'hcrop', 'restack', 'nmo', 'constant_sample_depth_spacing',
-                     'traveltime_to_depth', 'constant_space', 'elev_correct')
+                     'traveltime_to_depth', 'constant_space', 'elev_correct', 'clean_GPS')
 _saved = {}
 
 

@@ -591,3 +591,16 @@ def elev_correct(self, v_avg=1.69e8):
         self.picks.crop(-shift - 1)
     self.elevation = np.hstack((np.arange(top, bottom, -dz), bottom - self.nmo_depth))
     self.flags.elev = 1
+
+
+def clean_GPS(self):
+    """Fill GPS gaps by linear interpolation / extrapolation over the trace number; mirrors
+    _RadarDataProcessing.py:640-654 (O(tnum) host vectors only - the radargram is untouched)."""
+    from scipy.interpolate import interp1d
+    for name in ('x_coord', 'y_coord', 'decday', 'lat', 'long', 'elev'):
+        vec = getattr(self, name, None)
+        if vec is None:
+            continue
+        ok = np.isfinite(vec)
+        setattr(self, name, interp1d(self.trace_num[ok], vec[ok], fill_value="extrapolate",
+                                     assume_sorted=True)(self.trace_num))

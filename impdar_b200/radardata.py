@@ -103,3 +103,4 @@ class RadarData(object):
     traveltime_to_depth = processing.traveltime_to_depth
     constant_space = processing.constant_space
     elev_correct = processing.elev_correct
+    clean_GPS = processing.clean_GPS

@@ -417,3 +417,29 @@ def test_gpu_interp_kernels_reproduce_scipy_and_numpy(seed):
     assert np.array_equal(got_c, want.T, equal_nan=True)
     got_c32 = processing.interp_cols_device(Yd32.t().contiguous(), 'f32_f64', torch.float64, ns, 0).cpu().numpy()
     assert np.array_equal(got_c32, want32.T, equal_nan=True)
+
+
+def test_clean_gps_fills_gaps_like_reference():
+    g = np.load(os.path.join(GOLDEN_DIR, 'proc_reverse_f64.npz'))
+    d = dat_from(g)
+    lat0, elev0 = d.lat.copy(), d.elev.copy()
+    d.lat[[5, 6, 40]] = np.nan
+    d.elev[[0, 159]] = np.nan                                  # both ends: extrapolated
+    d.y_coord = None
+    data_before = d.data.copy()
+    d.clean_GPS()
+    assert np.all(np.isfinite(d.lat)) and np.all(np.isfinite(d.elev)) and d.y_coord is None
+    assert np.array_equal(d.lat[:5], lat0[:5]) and np.allclose(d.lat[5], lat0[4] + (lat0[7] - lat0[4]) / 3)
+    assert np.allclose(d.elev[0], 2 * elev0[1] - elev0[2]) and np.array_equal(d.data, data_before)
+    from oracle._refimport import reference_available, import_reference
+    if reference_available():
+        _, RefRadarData, _ = import_reference()
+        r = RefRadarData(None)
+        r.trace_num = g['in_trace_num'].copy()
+        for name in ('x_coord', 'y_coord', 'decday', 'lat', 'long', 'elev'):
+            setattr(r, name, g['in_' + name].copy())
+        r.lat[[5, 6, 40]] = np.nan
+        r.elev[[0, 159]] = np.nan
+        r.y_coord = None
+        r.clean_GPS()
+        assert np.array_equal(r.lat, d.lat) and np.array_equal(r.elev, d.elev) and np.array_equal(r.long, d.long)
