@@ -121,6 +121,15 @@ def test_no_gpu_means_error_not_fallback():
         _dat().migrate(mtype='stolt')
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _dat().horizontalfilt(0, 10)
+    # every radargram pass of the index / resampling operations, the denoising filters and the host-to-host Kirchhoff
+    # call need the device as well: nothing computes on the CPU
+    for call in (lambda d: d.migrate(mtype='kirch'), lambda d: d.reverse(), lambda d: d.crop(2, 'top', 'snum'),
+                 lambda d: d.hcrop(3, 'left'), lambda d: d.restack(3), lambda d: d.nmo(0.),
+                 lambda d: d.denoise(noise=0.1), lambda d: d.denoise(ftype='median')):
+        d = _dat()
+        d.trig = np.zeros(d.tnum)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call(d)
 
 
 def test_kirchhoff_ranges_cover_and_balance():
