@@ -49,6 +49,10 @@ PROTOTYPES = {
                                       _vp, _c_sz, _vp]),
     "impdar_kirchhoff_rows_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_dbl, _c_int, _c_int, _c_int,
                                            _c_int, _c_int, _c_int, _vp, _c_sz, _vp]),
+    "impdar_kirchhoff_input_window": (_c_int, [_c_int, _c_int, _vp, _vp, _c_dbl, _c_int, _c_int, _vp, _vp]),
+    "impdar_kirchhoff_window_f32": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp,
+                                             _c_dbl, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_sz, _vp]),
+    "impdar_kirchhoff_last_tile_standdown": (_c_int, [_vp]),
     "impdar_kirchhoff_host_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int]),
     "impdar_kirchhoff_host_pipelined_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_dbl, _c_int, _c_int,
                                                      _vp, _c_sz, _vp]),

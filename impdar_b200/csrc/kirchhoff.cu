@@ -18,6 +18,10 @@
 //     so the picked sample is the reference's for every pair.
 //   * the aperture cut 2r/v > max(tt) is resolved exactly once per output sample (binary search with the
 //     float64 predicate over the ascending trace positions), so the inner loop only tests a trace range.
+#include <math.h>
+
+#include <mutex>
+
 #include "common.cuh"
 
 namespace impdar {
@@ -297,10 +301,11 @@ __global__ void __launch_bounds__(256) kirch_general_kernel(const __grid_constan
 }
 
 // d/dt with np.gradient's stencil (coefficients a,b,c per row; b == 0 in numpy's uniform branch, which
-// never touches f[s]) fused with the transpose to trace-major and a non-finite scan.
+// never touches f[s]) fused with the transpose to trace-major and a non-finite scan.  `data` holds ncols columns
+// with row stride ld; gradT / dataT are indexed by the local column.
 __global__ void __launch_bounds__(256) grad_transpose_kernel(const float *__restrict__ data,
                                                              float *__restrict__ gradT,
-                                                             float *__restrict__ dataT, int S, int T, int SP,
+                                                             float *__restrict__ dataT, int S, int ncols, int ld, int SP,
                                                              const double *__restrict__ coef,
                                                              int *__restrict__ flags) {
     __shared__ float tg[32][33];
@@ -310,13 +315,13 @@ __global__ void __launch_bounds__(256) grad_transpose_kernel(const float *__rest
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int s = s0 + r, x = x0 + threadIdx.x;
         float g = 0.f, dv = 0.f;
-        if (s < S && x < T) {
+        if (s < S && x < ncols) {
             const double a = coef[s], b = coef[S + s], c = coef[2 * S + s];
-            dv = data[(size_t)s * T + x];
+            dv = data[(size_t)s * ld + x];
             double acc = 0.0;
-            if (s > 0 && a != 0.0) acc += a * (double)data[(size_t)(s - 1) * T + x];
+            if (s > 0 && a != 0.0) acc += a * (double)data[(size_t)(s - 1) * ld + x];
             if (b != 0.0) acc += b * (double)dv;
-            if (s < S - 1 && c != 0.0) acc += c * (double)data[(size_t)(s + 1) * T + x];
+            if (s < S - 1 && c != 0.0) acc += c * (double)data[(size_t)(s + 1) * ld + x];
             g = (float)acc;
             if (!isfinite(g) || !isfinite(dv)) bad = true;
         }
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(256) grad_transpose_kernel(const float *__rest
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int x = x0 + r, s = s0 + threadIdx.x;
-        if (x < T && s < S) {
+        if (x < ncols && s < S) {
             gradT[(size_t)x * SP + s] = tg[threadIdx.x][r];
             if (dataT) dataT[(size_t)x * SP + s] = td[threadIdx.x][r];
         }
@@ -366,6 +371,7 @@ struct KirchTabParams {
     unsigned long long *stats;
     int S, T, Tp, Apad, A1, ldo, x_begin, x_end;
     int s_begin, s_end;  // output rows of this launch (the host pipeline runs the image in row chunks)
+    const int *only_if;  // non-null: the launch stands in for the tile kernel and runs only when *only_if or flags[0] is set
 };
 
 __global__ void __launch_bounds__(128) kirch_table_build_kernel(int2 *__restrict__ tab, float *__restrict__ tabn,
@@ -408,24 +414,26 @@ __global__ void __launch_bounds__(128) kirch_table_build_kernel(int2 *__restrict
     if (k == -2) amb_list[atomicAdd(amb_count, 1)] = ti * A1 + m;  // list has room for every entry
 }
 
-// d/dt (np.gradient stencil) into the padded row-major layout; also the non-finite scan.
+// d/dt (np.gradient stencil) into the padded row-major layout; also the non-finite scan.  `data` holds the radargram
+// columns [c0, c0 + ncols) with row stride ld (the whole image: c0 = 0, ncols = ld = T); trace x lands at column
+// aoff + x of the padded image (aoff = Apad - c0).
 __global__ void __launch_bounds__(256) grad_padded_kernel(const float *__restrict__ data, float *__restrict__ gP,
-                                                          float *__restrict__ dP, int S, int T, int Tp, int Apad,
-                                                          const double *__restrict__ coef, int *__restrict__ flags,
-                                                          int s0) {
+                                                          float *__restrict__ dP, int S, int c0, int ncols, int ld,
+                                                          int Tp, int aoff, const double *__restrict__ coef,
+                                                          int *__restrict__ flags, int s0) {
     const int s = s0 + blockIdx.y;
     const double a = coef[s], b = coef[S + s], c = coef[2 * S + s];
     bool bad = false;
-    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < T; x += gridDim.x * blockDim.x) {
-        const float dv = data[(size_t)s * T + x];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ncols; j += gridDim.x * blockDim.x) {
+        const float dv = data[(size_t)s * ld + j];
         double acc = 0.0;
-        if (s > 0 && a != 0.0) acc += a * (double)data[(size_t)(s - 1) * T + x];
+        if (s > 0 && a != 0.0) acc += a * (double)data[(size_t)(s - 1) * ld + j];
         if (b != 0.0) acc += b * (double)dv;
-        if (s < S - 1 && c != 0.0) acc += c * (double)data[(size_t)(s + 1) * T + x];
+        if (s < S - 1 && c != 0.0) acc += c * (double)data[(size_t)(s + 1) * ld + j];
         const float g = (float)acc;
         if (!isfinite(g) || !isfinite(dv)) bad = true;
-        gP[(size_t)s * Tp + Apad + x] = g;
-        if (dP) dP[(size_t)s * Tp + Apad + x] = dv;
+        gP[(size_t)s * Tp + aoff + c0 + j] = g;
+        if (dP) dP[(size_t)s * Tp + aoff + c0 + j] = dv;
     }
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, 1);
 }
@@ -495,6 +503,7 @@ __device__ __forceinline__ void kirch_table_loop(const KirchTabParams &p, int ti
 
 template <bool NEAR, bool STATS>
 __global__ void __launch_bounds__(128) kirch_table_kernel(const __grid_constant__ KirchTabParams p) {
+    if (p.only_if && !(p.only_if[0] | p.flags[0])) return;   // the tile kernel has done these rows
     const int ti = p.s_begin + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int xbase = p.x_begin + (blockIdx.y * 4 + warp) * (32 * KT_R) + lane;
@@ -552,6 +561,10 @@ __global__ void __launch_bounds__(256) kirch_table_fixup_kernel(const __grid_con
     }
 }
 
+}  // namespace impdar
+#include "kirchhoff_tile.cuh"
+namespace impdar {
+
 static inline int kirch_sp(int S) { return ((S + 64 + 31) / 32) * 32; }
 
 // float32 rows -> float64 rows (the reference returns float64, mig_python.py:95/:118); runs on the download stream
@@ -578,29 +591,46 @@ struct KirchPipe {
 struct KirchRows {
     int s_begin, s_end, g_hi;
 };
-static KirchPipe g_pipe;
-static int g_pipe_dev = -1;
-static int kirch_pipe_streams() {
+// Column window of the input (impdar_kirchhoff_window_f32): `data` holds radargram columns [col0, col0 + ncols), row
+// stride ld; `out` has row stride ldo.
+struct KirchWindow {
+    int col0, ncols, ld, ldo;
+};
+// Side streams and events of the host pipeline: one set per device, created on first use under a lock.  Selection
+// switches and "last call" records are per host thread (one host thread - or process - per GPU).
+constexpr int KP_MAX_DEVICES = 64;
+static KirchPipe g_pipes[KP_MAX_DEVICES];
+static bool g_pipe_ready[KP_MAX_DEVICES];
+static std::mutex g_pipe_mu;
+static int kirch_pipe_streams(KirchPipe **out) {
     int dev = 0;
     IMPDAR_CUDA(cudaGetDevice(&dev));
-    if (g_pipe_dev == dev) return IMPDAR_B200_OK;
-    IMPDAR_CUDA(cudaStreamCreateWithFlags(&g_pipe.up, cudaStreamNonBlocking));
-    IMPDAR_CUDA(cudaStreamCreateWithFlags(&g_pipe.down, cudaStreamNonBlocking));
-    for (int i = 0; i < KP_MAX_CHUNKS; ++i) {
-        IMPDAR_CUDA(cudaEventCreateWithFlags(&g_pipe.ev_up[i], cudaEventDisableTiming));
-        IMPDAR_CUDA(cudaEventCreateWithFlags(&g_pipe.ev_done[i], cudaEventDisableTiming));
+    IMPDAR_CHECK_ARG(dev >= 0 && dev < KP_MAX_DEVICES, "kirchhoff_host_pipelined: device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    KirchPipe &pp = g_pipes[dev];
+    if (!g_pipe_ready[dev]) {
+        IMPDAR_CUDA(cudaStreamCreateWithFlags(&pp.up, cudaStreamNonBlocking));
+        IMPDAR_CUDA(cudaStreamCreateWithFlags(&pp.down, cudaStreamNonBlocking));
+        for (int i = 0; i < KP_MAX_CHUNKS; ++i) {
+            IMPDAR_CUDA(cudaEventCreateWithFlags(&pp.ev_up[i], cudaEventDisableTiming));
+            IMPDAR_CUDA(cudaEventCreateWithFlags(&pp.ev_done[i], cudaEventDisableTiming));
+        }
+        IMPDAR_CUDA(cudaEventCreateWithFlags(&pp.ev_entry, cudaEventDisableTiming));
+        IMPDAR_CUDA(cudaEventCreateWithFlags(&pp.ev_exit, cudaEventDisableTiming));
+        g_pipe_ready[dev] = true;
     }
-    IMPDAR_CUDA(cudaEventCreateWithFlags(&g_pipe.ev_entry, cudaEventDisableTiming));
-    IMPDAR_CUDA(cudaEventCreateWithFlags(&g_pipe.ev_exit, cudaEventDisableTiming));
-    g_pipe_dev = dev;
+    *out = &pp;
     return IMPDAR_B200_OK;
 }
 
-static unsigned long long *g_last_stats = nullptr;
-static cudaStream_t g_last_stats_stream = nullptr;
-static int g_stats_enabled = 0;
-static int g_kirch_mode = 0;   // 0 auto, 1 general, 2 table
-static int g_last_path = 0;
+static thread_local unsigned long long *g_last_stats = nullptr;
+static thread_local const int *g_last_flags = nullptr;
+static thread_local cudaStream_t g_last_stats_stream = nullptr;
+static thread_local int g_stats_enabled = 0;
+static thread_local int g_kirch_mode = 0;   // 0 auto, 1 general, 2 table path (tile kernel where it applies), 3 table path, gather kernel only
+static thread_local int g_last_path = 0;    // 1 general, 2 table (gather kernel), 3 table (tile kernel launched)
+
+static bool g_tile_attr[KP_MAX_DEVICES];
 
 }  // namespace impdar
 
@@ -610,24 +640,62 @@ extern "C" {
 
 static inline size_t kirch_roundup(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Farthest trace offset a pair can have on a uniform grid of spacing dxm: 2 r / v <= tmax  =>  m dxm <= v tmax / 2
+static inline int kirch_amax(int T, double vel, double tmax, double dxm) {
+    int Amax = (int)fmin((double)(T - 1), floor(vel * tmax / 2.0 / dxm) + 2.0);
+    return Amax < 0 ? 0 : Amax;
+}
+
 size_t impdar_kirchhoff_workspace_bytes(int S, int T, int nearfield) {
     const size_t nf = nearfield ? 2 : 1;
     // general path: trace-major d/dt (and data) with padded samples and 32 spare traces
     const size_t general = (size_t)(T + 32) * (size_t)kirch_sp(S) * sizeof(float) * nf;
-    // uniform-geometry path, worst case aperture = the whole profile: padded row-major image(s) + tables
+    // uniform-geometry path, worst case aperture = the whole profile: padded row-major image(s) + tables + schedule
     const size_t tp = kirch_roundup((size_t)T + 2 * kirch_roundup((size_t)T, 32), 32);
-    const size_t table = ((size_t)S * tp + 1024) * sizeof(float) * nf + (size_t)S * (size_t)T * (sizeof(int2) + sizeof(int) + (nearfield ? 4 : 0)) +
-                         (size_t)S * sizeof(int);
+    const size_t nblk = (size_t)(S + KT_Q - 1) / KT_Q + KP_MAX_CHUNKS;
+    const size_t table = ((size_t)S * tp + 4096) * sizeof(float) * nf + (size_t)S * (size_t)T * (sizeof(int2) + sizeof(int) + (nearfield ? 4 : 0)) +
+                         (size_t)S * sizeof(int) + nblk * ((size_t)S * sizeof(int2) + sizeof(int)) + 1024;
     size_t b = general > table ? general : table;
     b += 6 * (size_t)S * sizeof(double);  // zs, zs2, tt, grad coefficients
     b += (size_t)T * sizeof(double);      // dist
     return b + 4096;
 }
 
+int impdar_kirchhoff_input_window(int S, int T, const double *dist_m, const double *tt_s, double vel, int x_begin,
+                                  int x_end, int *col0, int *col1) {
+    IMPDAR_CHECK_ARG(dist_m && tt_s && col0 && col1, "kirchhoff_input_window: null pointer");
+    IMPDAR_CHECK_ARG(S >= 2 && T >= 1 && 0 <= x_begin && x_begin < x_end && x_end <= T, "kirchhoff_input_window: bad range");
+    double tmax = tt_s[0];
+    for (int i = 1; i < S; ++i) tmax = fmax(tmax, tt_s[i]);
+    bool monotone = true;
+    for (int i = 1; i < T; ++i)
+        if (!(dist_m[i] >= dist_m[i - 1])) { monotone = false; break; }
+    *col0 = 0;
+    *col1 = T;
+    if (!monotone || !(tmax > 0.0) || T < 2) return IMPDAR_B200_OK;
+    // by distance (any monotone geometry): |d| <= v tmax / 2, with a relative margin and two traces of slack
+    const double reach = vel * tmax / 2.0 * (1.0 + 1e-9);
+    int lo = x_begin, hi = x_end - 1;
+    while (lo > 0 && dist_m[x_begin] - dist_m[lo - 1] <= reach) --lo;
+    while (hi < T - 1 && dist_m[hi + 1] - dist_m[x_end - 1] <= reach) ++hi;
+    // by trace count on the fitted uniform grid (what the table path reads): Amax offsets each side
+    const double dxm = (dist_m[T - 1] - dist_m[0]) / (double)(T - 1);
+    if (dxm > 0.0) {
+        const int Amax = kirch_amax(T, vel, tmax, dxm);
+        lo = lo < x_begin - Amax ? lo : x_begin - Amax;
+        hi = hi > x_end - 1 + Amax ? hi : x_end - 1 + Amax;
+    }
+    lo -= 2;
+    hi += 2;
+    *col0 = lo < 0 ? 0 : lo;
+    *col1 = hi + 1 > T ? T : hi + 1;
+    return IMPDAR_B200_OK;
+}
+
 static int kirchhoff_impl(const float *data, float *out, int S, int T, const double *dist_m, const double *tt_s,
                           const double *grad_coef, double vel, int nearfield, int x_begin, int x_end,
                           void *workspace, size_t ws_bytes, void *stream, const KirchPipe *pipe,
-                          const KirchRows *rows = nullptr) {
+                          const KirchRows *rows = nullptr, const KirchWindow *win = nullptr) {
     IMPDAR_CHECK_ARG(data && out && dist_m && tt_s && grad_coef, "kirchhoff: null pointer");
     IMPDAR_CHECK_ARG(S >= 2 && T >= 1, "kirchhoff: need snum >= 2, tnum >= 1");
     IMPDAR_CHECK_ARG(0 <= x_begin && x_begin < x_end && x_end <= T, "kirchhoff: bad output range [%d, %d)",
@@ -637,6 +705,18 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
     const size_t need = impdar_kirchhoff_workspace_bytes(S, T, nearfield);
     IMPDAR_CHECK_ARG(workspace && ws_bytes >= need, "kirchhoff: workspace too small (%zu < %zu)", ws_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
+    const int c0 = win ? win->col0 : 0, ncols = win ? win->ncols : T, ld = win ? win->ld : T;
+    const int ldo = win ? win->ldo : x_end - x_begin;
+    if (win) {
+        IMPDAR_CHECK_ARG(c0 >= 0 && ncols >= 1 && c0 + ncols <= T && ld >= ncols && ldo >= x_end - x_begin,
+                         "kirchhoff_window: bad column window [%d, %d) / strides", c0, c0 + ncols);
+        int need0 = 0, need1 = T;
+        int rcw = impdar_kirchhoff_input_window(S, T, dist_m, tt_s, vel, x_begin, x_end, &need0, &need1);
+        if (rcw) return rcw;
+        IMPDAR_CHECK_ARG(c0 <= need0 && c0 + ncols >= need1,
+                         "kirchhoff_window: output traces [%d, %d) read input columns [%d, %d), the window holds [%d, %d)",
+                         x_begin, x_end, need0, need1, c0, c0 + ncols);
+    }
 
     const double *h_tt = tt_s, *h_dist = dist_m;  // HOST vectors (small); device copies live in the workspace
     double tmax = h_tt[0];
@@ -674,8 +754,9 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
     }
     const double eps_t = (2.0 / vel) * (2.0 * maxdev_d) + 1e-15 * (fabs(tmax) + fabs(tt0));
     const bool uniform_ok = monotone && T > 1 && dxm > 0.0 && tmax > 0.0 && eps_t / dt_eff < 1e-5;
-    IMPDAR_CHECK_ARG(!(g_kirch_mode == 2 && !uniform_ok), "kirchhoff: table path forced but trace spacing is not uniform");
-    const bool use_table = (g_kirch_mode == 2) || (g_kirch_mode == 0 && uniform_ok);
+    IMPDAR_CHECK_ARG(!(g_kirch_mode >= 2 && !uniform_ok), "kirchhoff: table path forced but trace spacing is not uniform");
+    const bool use_table = (g_kirch_mode >= 2) || (g_kirch_mode == 0 && uniform_ok);
+    IMPDAR_CHECK_ARG(!(win && !monotone), "kirchhoff_window: trace positions must be ascending");
 
     // carve workspace: small vectors first
     char *w = (char *)workspace;
@@ -690,15 +771,15 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
     w += 3 * (size_t)S * sizeof(double);
     double *d_dist = (double *)w;
     w += (size_t)T * sizeof(double);
-    int *flags = (int *)w;
-    unsigned long long *stats = (unsigned long long *)(w + 64);
+    int *flags = (int *)w;                         // [0] non-finite input, [8] ambiguous-entry count, [16] tile stand-down
+    unsigned long long *stats = (unsigned long long *)(w + 128);
     w += 256;
     w = (char *)(((uintptr_t)w + 255) & ~(uintptr_t)255);
     IMPDAR_CUDA(cudaMemcpyAsync(d_tt, tt_s, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
     IMPDAR_CUDA(cudaMemcpyAsync(d_coef, grad_coef, 3 * (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
     IMPDAR_CUDA(cudaMemcpyAsync(d_dist, dist_m, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, st));
     const bool continuing = rows && rows->g_hi < S;   // later call of a bottom-up row sequence: flags, tables, d/dt rows stay
-    if (!continuing) IMPDAR_CUDA(cudaMemsetAsync(flags, 0, 128, st));
+    if (!continuing) IMPDAR_CUDA(cudaMemsetAsync(flags, 0, 256, st));
     kirch_prep_vectors_kernel<<<(S + 255) / 256, 256, 0, st>>>(d_tt, zs, zs2, S, vel);
     IMPDAR_LAUNCH_CHECK();
 
@@ -706,20 +787,21 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
     memset(&p, 0, sizeof(p));
     p.out = out; p.dist = d_dist; p.tt = d_tt; p.zs = zs; p.zs2 = zs2;
     p.flags = flags; p.stats = stats;
-    p.S = S; p.T = T; p.ldo = x_end - x_begin; p.x_begin = x_begin; p.x_end = x_end;
+    p.S = S; p.T = T; p.ldo = ldo; p.x_begin = x_begin; p.x_end = x_end;
     p.vel = vel; p.tmax = tmax; p.tt0 = tt0; p.inv_dt = 1.0 / dt_eff; p.cs = 2.0 / (vel * dt_eff);
     p.neg_u0 = (float)(-u0); p.thr = thr;
     p.wfar = (float)(1.0 / (2.0 * 3.14159265358979323846 * vel));
     p.wnear = (float)(4.0 / ((vel * dt_eff) * (vel * dt_eff)) / (2.0 * 3.14159265358979323846));
     p.monotone = monotone;
+    int path = 1;
 
     if (use_table) {
-        int Amax = (int)fmin((double)(T - 1), floor(vel * tmax / 2.0 / dxm) + 2.0);
-        if (Amax < 0) Amax = 0;
+        const int Amax = kirch_amax(T, vel, tmax, dxm);
         const int A1 = Amax + 1;
         const int Apad = (int)kirch_roundup((size_t)Amax, 32);
-        const int Tp = (int)kirch_roundup((size_t)T + 2 * (size_t)Apad, 32);
-        const size_t img = ((size_t)S * Tp + 4 * 32 * KT_R + 32) * sizeof(float);  // + one tile of slack after the last row
+        const int Tp = (int)kirch_roundup((size_t)ncols + 2 * (size_t)Apad, 32);
+        const int aoff = Apad - c0;                                     // trace x lives at padded column aoff + x
+        const size_t img = ((size_t)S * Tp + 4096) * sizeof(float);    // + slack after the last row (tiles overhang)
         float *gP = (float *)w;
         w += img;
         float *dP = nullptr;
@@ -739,6 +821,18 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
         int *amb_list = (int *)w;
         w += (size_t)S * A1 * sizeof(int);
         int *amb_count = flags + 8;
+        int *sched_flags = flags + 16;
+        w = (char *)(((uintptr_t)w + 255) & ~(uintptr_t)255);
+        const bool use_tile = !nearfield && g_kirch_mode != 3;
+        const int nchunks = pipe ? pipe->nchunks : 1;
+        const size_t nblk_max = (size_t)(S + KT_Q - 1) / KT_Q + nchunks;
+        int2 *seg = (int2 *)w;
+        int *nstage = nullptr;
+        if (use_tile) {
+            w += nblk_max * (size_t)S * sizeof(int2);
+            nstage = (int *)w;
+            w += nblk_max * sizeof(int);
+        }
         IMPDAR_CHECK_ARG((unsigned long long)S * (unsigned long long)A1 < (1ull << 31), "kirchhoff: table too large");
         IMPDAR_CHECK_ARG((size_t)(w - (char *)workspace) <= ws_bytes, "kirchhoff: workspace too small for the table path");
         if (!continuing) {
@@ -749,15 +843,25 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
                                                           1.0 / dt_eff, eps_t, amb_list, amb_count);
             IMPDAR_LAUNCH_CHECK();
         }
+        if (use_tile) {
+            int dev = 0;
+            IMPDAR_CUDA(cudaGetDevice(&dev));
+            if (dev >= 0 && dev < KP_MAX_DEVICES && !g_tile_attr[dev]) {
+                IMPDAR_CUDA(cudaFuncSetAttribute(kirch_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT_SMEM));
+                g_tile_attr[dev] = true;
+            }
+        }
         KirchTabParams tp;
         tp.gP = gP; tp.dP = dP; tp.tab = tab; tp.tabn = tabn; tp.nm = nm; tp.out = out; tp.flags = flags;
-        tp.stats = stats; tp.S = S; tp.T = T; tp.Tp = Tp; tp.Apad = Apad; tp.A1 = A1; tp.ldo = x_end - x_begin;
+        tp.stats = stats; tp.S = S; tp.T = T; tp.Tp = Tp; tp.Apad = aoff; tp.A1 = A1; tp.ldo = ldo;
         tp.x_begin = x_begin; tp.x_end = x_end;
-        p.gradT = gP; p.dataT = dP; p.rowmajor = 1; p.Tp = Tp; p.Apad = Apad;
+        tp.only_if = use_tile ? sched_flags : nullptr;
+        p.gradT = gP; p.dataT = dP; p.rowmajor = 1; p.Tp = Tp; p.Apad = aoff;
+        path = use_tile ? 3 : 2;
         // Row chunks, bottom-up.  Without a host pipeline this is one chunk covering the whole image.
-        const int nchunks = pipe ? pipe->nchunks : 1;
         int g_hi = rows ? rows->g_hi : S;   // d/dt rows [g_hi, S) are built
         int u_hi = S;   // input rows [u_hi, S) are uploaded
+        size_t blk_used = 0;
         for (int j = nchunks - 1; j >= 0; --j) {
             const int r0 = rows ? rows->s_begin : (int)((long long)S * j / nchunks);
             const int r1 = rows ? rows->s_end : (int)((long long)S * (j + 1) / nchunks);
@@ -776,23 +880,39 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
             {
                 const int g0 = r0;   // row r0 - 1 is uploaded (or r0 == 0: one-sided stencil)
                 if (g0 < g_hi) {
-                    int gx = (T + 255) / 256;
+                    int gx = (ncols + 255) / 256;
                     if (gx > 64) gx = 64;
                     dim3 grid(gx, g_hi - g0);
-                    grad_padded_kernel<<<grid, 256, 0, st>>>(data, gP, dP, S, T, Tp, Apad, d_coef, flags, g0);
+                    grad_padded_kernel<<<grid, 256, 0, st>>>(data, gP, dP, S, c0, ncols, ld, Tp, aoff, d_coef, flags, g0);
                     IMPDAR_LAUNCH_CHECK();
                     g_hi = g0;
                 }
             }
             tp.s_begin = r0; tp.s_end = r1;
-            dim3 grid(r1 - r0, (x_end - x_begin + 4 * 32 * KT_R - 1) / (4 * 32 * KT_R));
             if (g_stats_enabled) {
-                if (nearfield) { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<true, true><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
-                else { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<false, true><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
-            } else {
-                if (nearfield) { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<true, false><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
-                else { ktimer_begin("kirch_table_kernel", st); kirch_table_kernel<false, false><<<grid, 128, 0, st>>>(tp); ktimer_end(st); }
+                kirch_table_count_kernel<<<r1 - r0, 256, 0, st>>>(tab, nm, A1, T, x_begin, x_end, r0, stats);
+                IMPDAR_LAUNCH_CHECK();
             }
+            if (use_tile) {
+                const int nblk = (r1 - r0 + KT_Q - 1) / KT_Q;
+                KirchTileParams tq;
+                tq.seg = seg + blk_used * (size_t)S;
+                tq.nstage = nstage + blk_used;
+                tq.sched_flags = sched_flags;
+                blk_used += (size_t)nblk;
+                kirch_tile_sched_kernel<<<nblk, 256, 0, st>>>(tab, nm, S, A1, r0, r1, (int2 *)tq.seg, (int *)tq.nstage, sched_flags);
+                IMPDAR_LAUNCH_CHECK();
+                dim3 tgrid(nblk, (x_end - x_begin + KT_X - 1) / KT_X);
+                ktimer_begin("kirch_tile_kernel", st);
+                kirch_tile_kernel<<<tgrid, KT_THREADS, KT_SMEM, st>>>(tp, tq);
+                ktimer_end(st);
+                IMPDAR_LAUNCH_CHECK();
+            }
+            dim3 grid(r1 - r0, (x_end - x_begin + 4 * 32 * KT_R - 1) / (4 * 32 * KT_R));
+            ktimer_begin("kirch_table_kernel", st);
+            if (nearfield) kirch_table_kernel<true, false><<<grid, 128, 0, st>>>(tp);
+            else kirch_table_kernel<false, false><<<grid, 128, 0, st>>>(tp);
+            ktimer_end(st);
             IMPDAR_LAUNCH_CHECK();
             // exact pass over flagged table entries of these rows (reads the same padded row-major images)
             if (nearfield) kirch_table_fixup_kernel<true><<<num_sms() * 2, 256, 0, st>>>(tp, p, amb_list, amb_count);
@@ -812,10 +932,10 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
         }
     } else {
         IMPDAR_CHECK_ARG(!rows, "kirchhoff_rows: row-range calls need uniform trace spacing (the table path)");
-        IMPDAR_CHECK_ARG((unsigned long long)(T + 32) * (unsigned long long)kirch_sp(S) < (1ull << 32),
+        IMPDAR_CHECK_ARG((unsigned long long)(ncols + 32) * (unsigned long long)kirch_sp(S) < (1ull << 32),
                          "kirchhoff: (tnum + 32) * padded snum must stay below 2^32 elements");
         const int SP = kirch_sp(S);
-        const size_t tbytes = (size_t)(T + 32) * SP * sizeof(float);  // 32 zero rows: chunks are padded to 4 traces
+        const size_t tbytes = (size_t)(ncols + 32) * SP * sizeof(float);  // 32 zero rows: chunks are padded to 4 traces
         float *gradT = (float *)w;
         w += tbytes;
         float *dataT = nullptr;
@@ -827,11 +947,14 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
         if (pipe)  // irregular geometry: no row pipeline, the whole input goes up first
             IMPDAR_CUDA(cudaMemcpyAsync(pipe->d_in, pipe->h_in, (size_t)S * T * sizeof(float), cudaMemcpyHostToDevice, st));
         {
-            dim3 grid((T + 31) / 32, (S + 31) / 32), block(32, 8);
-            grad_transpose_kernel<<<grid, block, 0, st>>>(data, gradT, dataT, S, T, SP, d_coef, flags);
+            dim3 grid((ncols + 31) / 32, (S + 31) / 32), block(32, 8);
+            grad_transpose_kernel<<<grid, block, 0, st>>>(data, gradT, dataT, S, ncols, ld, SP, d_coef, flags);
             IMPDAR_LAUNCH_CHECK();
         }
-        p.gradT = gradT; p.dataT = dataT; p.SP = SP;
+        // the kernel indexes traces globally: shift the bases so that trace x reads local column x - c0.  Its loops
+        // stay inside the exact aperture, which the window covers (checked above); chunks of 4 traces may run up to 3
+        // traces past it into the zero rows / the next traces, with zero weight.
+        p.gradT = gradT - (size_t)c0 * SP; p.dataT = dataT ? dataT - (size_t)c0 * SP : nullptr; p.SP = SP;
         dim3 grid((S + 31) / 32, (x_end - x_begin + 7) / 8), block(32, 8);
         if (g_stats_enabled) {
             if (nearfield) { ktimer_begin("kirch_general_kernel", st); kirch_general_kernel<true, true><<<grid, block, 0, st>>>(p); ktimer_end(st); }
@@ -849,8 +972,9 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
         }
     }
     g_last_stats = stats;
+    g_last_flags = flags;
     g_last_stats_stream = st;
-    g_last_path = use_table ? 2 : 1;
+    g_last_path = path;
     return IMPDAR_B200_OK;
 }
 
@@ -871,6 +995,21 @@ int impdar_kirchhoff_rows_f32(const float *data, float *out, int S, int T, const
                           stream, nullptr, &rows);
 }
 
+int impdar_kirchhoff_window_f32(const float *data, int col0, int ncols, int ld, float *out, int ldo, int S, int T,
+                                const double *dist_m, const double *tt_s, const double *grad_coef, double vel,
+                                int nearfield, int x_begin, int x_end, int s_begin, int s_end, int g_hi, void *workspace,
+                                size_t ws_bytes, void *stream) {
+    KirchWindow win = {col0, ncols, ld, ldo};
+    if (s_begin == 0 && s_end == S && g_hi == S)   // whole image: any geometry
+        return kirchhoff_impl(data, out, S, T, dist_m, tt_s, grad_coef, vel, nearfield, x_begin, x_end, workspace,
+                              ws_bytes, stream, nullptr, nullptr, &win);
+    IMPDAR_CHECK_ARG(0 <= s_begin && s_begin < s_end && s_end <= S && s_end <= g_hi && g_hi <= S,
+                     "kirchhoff_window: need 0 <= s_begin < s_end <= g_hi <= snum, got [%d, %d), g_hi %d", s_begin, s_end, g_hi);
+    KirchRows rows = {s_begin, s_end, g_hi};
+    return kirchhoff_impl(data, out, S, T, dist_m, tt_s, grad_coef, vel, nearfield, x_begin, x_end, workspace, ws_bytes,
+                          stream, nullptr, &rows, &win);
+}
+
 size_t impdar_kirchhoff_host_workspace_bytes(int S, int T, int nearfield) {
     const size_t n = (size_t)S * (size_t)T;
     return impdar_kirchhoff_workspace_bytes(S, T, nearfield) + n * (2 * sizeof(float) + sizeof(double)) + 1024;
@@ -884,12 +1023,13 @@ int impdar_kirchhoff_host_pipelined_f64(const float *h_data, double *h_out, int 
     IMPDAR_CHECK_ARG(nchunks >= 1 && nchunks <= KP_MAX_CHUNKS, "kirchhoff_host_pipelined: nchunks must be in [1, %d]", KP_MAX_CHUNKS);
     const size_t need = impdar_kirchhoff_host_workspace_bytes(S, T, nearfield);
     IMPDAR_CHECK_ARG(workspace && ws_bytes >= need, "kirchhoff_host_pipelined: workspace too small (%zu < %zu)", ws_bytes, need);
-    int rc = kirch_pipe_streams();
+    KirchPipe *dev_pipe = nullptr;
+    int rc = kirch_pipe_streams(&dev_pipe);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)S * (size_t)T;
     char *w = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    KirchPipe pipe = g_pipe;
+    KirchPipe pipe = *dev_pipe;
     pipe.h_in = h_data;
     pipe.h_out = h_out;
     pipe.d_stage = (double *)w;
@@ -914,7 +1054,8 @@ int impdar_kirchhoff_host_pipelined_f64(const float *h_data, double *h_out, int 
 }
 
 int impdar_kirchhoff_set_mode(int mode) {
-    IMPDAR_CHECK_ARG(mode >= 0 && mode <= 2, "kirchhoff_set_mode: 0 auto, 1 general kernel, 2 uniform-geometry table kernel");
+    IMPDAR_CHECK_ARG(mode >= 0 && mode <= 3, "kirchhoff_set_mode: 0 auto, 1 general kernel, 2 uniform-geometry table path, "
+                                             "3 table path with the global-gather kernel only");
     g_kirch_mode = mode;
     return IMPDAR_B200_OK;
 }
@@ -933,6 +1074,15 @@ int impdar_kirchhoff_last_stats(unsigned long long *pairs, unsigned long long *e
     IMPDAR_CUDA(cudaStreamSynchronize(g_last_stats_stream));
     if (pairs) *pairs = h[0];
     if (exact_pairs) *exact_pairs = h[1];
+    return IMPDAR_B200_OK;
+}
+
+int impdar_kirchhoff_last_tile_standdown(int *stood_down) {
+    IMPDAR_CHECK_ARG(stood_down && g_last_flags, "kirchhoff_last_tile_standdown: no previous call");
+    int h[17] = {0};
+    IMPDAR_CUDA(cudaMemcpyAsync(h, g_last_flags, sizeof(h), cudaMemcpyDeviceToHost, g_last_stats_stream));
+    IMPDAR_CUDA(cudaStreamSynchronize(g_last_stats_stream));
+    *stood_down = (g_last_path != 3) ? -1 : ((h[0] | h[16]) ? 1 : 0);
     return IMPDAR_B200_OK;
 }
 

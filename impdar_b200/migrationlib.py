@@ -117,6 +117,49 @@ def kirchhoff_rows_device(data_dev, travel_time_us, dist_km, vel, nearfield, x_b
     return out
 
 
+def kirchhoff_input_window(snum, travel_time_us, dist_km, vel, x_begin, x_end):
+    """[col0, col1): the input columns the output traces [x_begin, x_end) can read (the range plus one aperture each
+    side; impdar_kirchhoff_input_window).  Host arithmetic only."""
+    lib = _lib.load()
+    tt_sec = device.host_f64(travel_time_us) / 1.0e6
+    dist_m = np.ascontiguousarray(device.host_f64(dist_km) * 1.0e3)
+    c0, c1 = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.check(lib.impdar_kirchhoff_input_window(int(snum), len(dist_m), device.ptr(dist_m), device.ptr(tt_sec), float(vel),
+                                                 int(x_begin), int(x_end), ctypes.byref(c0), ctypes.byref(c1)))
+    return c0.value, c1.value
+
+
+def kirchhoff_window_device(win_dev, col0, tnum, travel_time_us, dist_km, vel, nearfield, x_begin, x_end, out=None,
+                            rows=None):
+    """Kirchhoff on a COLUMN WINDOW of the radargram (impdar_kirchhoff_window_f32, the unit of the multi-GPU halo
+    exchange): `win_dev` is a (snum, ncols) float32 CUDA tensor (last stride 1, any row stride) holding columns
+    [col0, col0 + ncols) of a tnum-trace radargram whose full geometry is given; returns / fills the
+    (snum, x_end - x_begin) block `out` (last stride 1, any row stride: a column slice of the final image works).
+    rows = (s_begin, s_end, g_hi) runs one chunk of a bottom-up row sequence (see kirchhoff_rows_device).  The result
+    equals kirchhoff_device on the whole image bit for bit."""
+    import torch
+    lib = _lib.load()
+    S, ncols = win_dev.shape
+    assert win_dev.stride(1) == 1
+    tt_sec = device.host_f64(travel_time_us) / 1.0e6
+    dist_m = np.ascontiguousarray(device.host_f64(dist_km) * 1.0e3)
+    if not np.all(np.diff(tt_sec) > 0):
+        raise ValueError('travel_time must be strictly ascending for Kirchhoff migration')
+    coef = gradient_coefficients(tt_sec)
+    if out is None:
+        out = torch.empty((S, x_end - x_begin), dtype=torch.float32, device=win_dev.device)
+    assert out.stride(1) == 1 and out.shape == (S, x_end - x_begin)
+    s_begin, s_end, g_hi = (0, S, S) if rows is None else rows
+    ws = device.workspace(lib.impdar_kirchhoff_workspace_bytes(S, int(tnum), int(bool(nearfield))))
+    rc = lib.impdar_kirchhoff_window_f32(device.ptr(win_dev), int(col0), int(ncols), int(win_dev.stride(0)),
+                                         device.ptr(out), int(out.stride(0)), S, int(tnum), device.ptr(dist_m),
+                                         device.ptr(tt_sec), device.ptr(coef), float(vel), int(bool(nearfield)),
+                                         int(x_begin), int(x_end), int(s_begin), int(s_end), int(g_hi),
+                                         device.ptr(ws), ws.numel(), device.current_stream_ptr())
+    _lib.check(rc)
+    return out
+
+
 def kirchhoff_host(data, travel_time_us, dist_km, vel, nearfield, nchunks=None):
     """Host numpy radargram -> host float64 migrated image with upload, kernels and download overlapped in row
     chunks (impdar_kirchhoff_host_pipelined_f64).  The result lives in page-locked memory owned by the array."""
@@ -171,18 +214,33 @@ def enable_kirchhoff_stats(on=True):
     _lib.check(_lib.load().impdar_kirchhoff_enable_stats(int(bool(on))))
 
 
-KIRCHHOFF_AUTO, KIRCHHOFF_GENERAL, KIRCHHOFF_TABLE = 0, 1, 2
+KIRCHHOFF_AUTO, KIRCHHOFF_GENERAL, KIRCHHOFF_TABLE, KIRCHHOFF_TABLE_GATHER = 0, 1, 2, 3
 
 
 def set_kirchhoff_mode(mode=KIRCHHOFF_AUTO):
-    """Kernel selection: AUTO picks the uniform-geometry table kernel when the trace spacing is uniform and the
-    general-geometry kernel otherwise; GENERAL / TABLE force one (TABLE raises ValueError on irregular spacing)."""
+    """Kernel selection: AUTO picks the uniform-geometry table path when the trace spacing is uniform and the
+    general-geometry kernel otherwise; GENERAL / TABLE force one (TABLE raises ValueError on irregular spacing).  On the
+    table path the far-field sum runs in the shared-memory tile kernel (kirchhoff_tile.cuh); TABLE_GATHER keeps the
+    global-gather table kernel for everything (A/B runs, and what near field / non-finite input use anyway)."""
     _lib.check(_lib.load().impdar_kirchhoff_set_mode(int(mode)))
 
 
 def kirchhoff_last_path():
-    """'general' or 'table': which kernel the last Kirchhoff call ran."""
-    return {1: 'general', 2: 'table'}.get(_lib.load().impdar_kirchhoff_last_path(), 'none')
+    """'general' or 'table': which path the last Kirchhoff call ran."""
+    return {1: 'general', 2: 'table', 3: 'table'}.get(_lib.load().impdar_kirchhoff_last_path(), 'none')
+
+
+def kirchhoff_last_kernel():
+    """'general', 'table_gather' or 'table_tile' - the kernel that did the far-field sum of the last call ('table_tile'
+    only if the tile kernel really did the work; it stands down for non-finite input and for hyperbola intervals wider
+    than its staged segments).  Synchronises the call's stream."""
+    lib = _lib.load()
+    path = lib.impdar_kirchhoff_last_path()
+    if path != 3:
+        return {1: 'general', 2: 'table_gather'}.get(path, 'none')
+    v = ctypes.c_int(0)
+    _lib.check(lib.impdar_kirchhoff_last_tile_standdown(ctypes.byref(v)), RuntimeError)
+    return 'table_gather' if v.value else 'table_tile'
 
 
 # -------------------------------------------------------------------------------------------- Stolt

@@ -134,18 +134,126 @@ def _kirchhoff_sharded_pipelined(x, travel_time_us, dist_km, vel, nearfield, ran
     return out
 
 
+def kirchhoff_input_windows(snum, tnum, ranges, travel_time_us, dist_km, vel, window_fn=None):
+    """[(col0, col1)] per rank: the input columns each output range can read (range + one aperture each side)."""
+    if window_fn is None:
+        from .migrationlib import kirchhoff_input_window as window_fn
+    return [window_fn(snum, travel_time_us, dist_km, vel, b, e) if e > b else (0, 0) for b, e in ranges]
+
+
+def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, world, group, src, ranges, windows,
+                            nchunks, compute_window, gather):
+    """Halo exchange: rank `src` holds the radargram; every other rank receives ONLY the columns its output range can
+    read (its window), bottom-up in row chunks, computes each chunk of its range as soon as the rows are there and
+    ships the finished rows to `src` (gather == 'src') while the next chunk runs.  Both exchanges are one
+    all_to_all_single per chunk with empty splits everywhere except from / to `src`.  Rank `src` computes straight
+    from its own image into the final one.  Returns the (snum, tnum) image on `src` (None elsewhere) for
+    gather == 'src', or this rank's (snum, range) block for gather False."""
+    import torch
+    import torch.distributed as dist
+    S, T = x.shape
+    xb, xe = ranges[rank]
+    c0, c1 = windows[rank]
+    chunks = row_chunks(S, nchunks)
+    dev, dt = x.device, x.dtype
+    empty = torch.empty(0, dtype=dt, device=dev)
+    is_src = rank == src
+    # ---- 1. input windows, every chunk enqueued up front (the collective stream runs them back to back)
+    win = x[:, c0:c1] if is_src else torch.empty((S, c1 - c0), dtype=dt, device=dev)
+    arrive = {}
+    u_hi = S
+    for j in reversed(range(len(chunks))):
+        u0 = max(chunks[j][0] - 1, 0)
+        if u0 >= u_hi:
+            arrive[j] = None
+            continue
+        rows = u_hi - u0
+        if is_src:
+            sizes = [0 if r == src else rows * (windows[r][1] - windows[r][0]) for r in range(world)]
+            send = torch.empty(sum(sizes), dtype=dt, device=dev)
+            off = 0
+            for r in range(world):
+                if sizes[r]:
+                    send[off:off + sizes[r]].view(rows, -1).copy_(x[u0:u_hi, windows[r][0]:windows[r][1]])
+                    off += sizes[r]
+            arrive[j] = dist.all_to_all_single(empty, send, [0] * world, sizes, group=group, async_op=True)
+        else:
+            recv = win[u0:u_hi].view(-1)
+            osz = [rows * (c1 - c0) if r == src else 0 for r in range(world)]
+            arrive[j] = dist.all_to_all_single(recv, empty, osz, [0] * world, group=group, async_op=True)
+        u_hi = u0
+    # ---- 2. chunk by chunk: wait for its rows, compute, ship the finished rows
+    out = torch.empty((S, T), dtype=dt, device=dev) if (is_src and gather) else None
+    block = out[:, xb:xe] if out is not None else torch.empty((S, max(xe - xb, 0)), dtype=dt, device=dev)
+    ship, stages = {}, {}
+    g_hi = S
+    for j in reversed(range(len(chunks))):
+        r0, r1 = chunks[j]
+        if arrive[j] is not None:
+            arrive[j].wait()                       # the compute stream waits; the host does not
+        if xe > xb:
+            compute_window(win, c0, T, travel_time_us, dist_km, vel, nearfield, xb, xe, block, (r0, r1, g_hi))
+            g_hi = r0
+        if gather:
+            rows = r1 - r0
+            if is_src:
+                sizes = [0 if r == src else rows * (ranges[r][1] - ranges[r][0]) for r in range(world)]
+                stages[j] = torch.empty(sum(sizes), dtype=dt, device=dev)
+                ship[j] = dist.all_to_all_single(stages[j], empty, sizes, [0] * world, group=group, async_op=True)
+            else:
+                isz = [rows * (xe - xb) if r == src else 0 for r in range(world)]
+                ship[j] = dist.all_to_all_single(empty, block[r0:r1].reshape(-1), [0] * world, isz, group=group,
+                                                 async_op=True)
+    if not gather:
+        return block
+    # ---- 3. rank src files the received rows into the image
+    for j in reversed(range(len(chunks))):
+        ship[j].wait()
+        if is_src:
+            r0, r1 = chunks[j]
+            off = 0
+            for r in range(world):
+                n = 0 if r == src else (r1 - r0) * (ranges[r][1] - ranges[r][0])
+                if n:
+                    out[r0:r1, ranges[r][0]:ranges[r][1]] = stages[j][off:off + n].view(r1 - r0, -1)
+                    off += n
+    return out
+
+
+def _spacing_is_uniform(travel_time_us, dist_km, vel):
+    """The table path's own criterion (csrc/kirchhoff.cu: uniform_ok), evaluated on the host from vectors every rank
+    has, so that all ranks take the same branch before any collective is issued."""
+    tt = np.asarray(travel_time_us, dtype=np.float64) / 1e6
+    d = np.asarray(dist_km, dtype=np.float64) * 1e3
+    T, S = len(d), len(tt)
+    if T < 2 or S < 2 or not np.all(np.diff(d) >= 0):
+        return False
+    dxm = (d[-1] - d[0]) / (T - 1)
+    tmax = tt.max()
+    if not (dxm > 0 and tmax > 0):
+        return False
+    dev = np.max(np.abs(d - (d[0] + np.arange(T) * dxm)))
+    dt_eff = (tt[-1] - tt[0]) / (S - 1)
+    eps_t = (2.0 / vel) * (2.0 * dev) + 1e-15 * (abs(tmax) + abs(tt[0]))
+    return bool(eps_t / dt_eff < 1e-5)
+
+
 def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=None, world=None, gather=True,
-                             compute=None, group=None, src=0, pipeline_chunks=4, compute_rows=None):
+                             compute=None, group=None, src=0, pipeline_chunks=4, compute_rows=None, exchange=None,
+                             compute_window=None, window_fn=None):
     """Kirchhoff migration of one radargram over all ranks of the process group.
 
-    x : (snum, tnum) float32 tensor on this rank's device; only rank `src`'s content matters (it is
-        broadcast to the others).  Returns the full (snum, tnum) migrated image on every rank if `gather`,
-        else this rank's (snum, x_end - x_begin) block and its range.
+    x : (snum, tnum) float32 tensor on this rank's device; only rank `src`'s content matters.
+    exchange = 'halo' (default with gather in ('src', False)): every rank receives only the input columns its output
+        range can read, and the output blocks go to rank `src` only (gather='src': returns the image there, None
+        elsewhere) or stay put (gather=False: returns (block, range)).  `x` is not written on the other ranks.
+    exchange = 'broadcast' (default with gather=True, the round-1 scheme): the whole input is broadcast into `x` and
+        the padded blocks are all-gathered, so every rank returns the full image.
     compute(x, travel_time_us, dist_km, vel, nearfield, x_begin, x_end) -> (snum, x_end-x_begin) tensor;
-    defaults to the CUDA kernel (tests on CPU/gloo inject their own).
-    pipeline_chunks > 1 (with `gather`): the broadcast, the kernels and the all-gather overlap in bottom-up row chunks
-    through compute_rows(x, tt, dist, vel, nearfield, x_begin, x_end, s_begin, s_end, g_hi, out) - the CUDA row-range
-    entry by default; irregular trace spacing falls back to the three phases back to back."""
+    defaults to the CUDA kernel (tests on CPU/gloo inject their own), likewise compute_rows (row-range entry) and
+    compute_window(win, col0, tnum, tt, dist, vel, nearfield, x_begin, x_end, out, rows) (column-window entry).
+    pipeline_chunks > 1: the exchanges and the kernels overlap in bottom-up row chunks (uniform trace spacing; decided
+    on the host identically on every rank - irregular spacing runs the phases back to back)."""
     import torch
     import torch.distributed as dist
     default_compute = compute is None
@@ -155,14 +263,31 @@ def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=No
     if compute_rows is None and default_compute:
         from .migrationlib import kirchhoff_rows_device
         compute_rows = kirchhoff_rows_device
+    if compute_window is None and default_compute:
+        from .migrationlib import kirchhoff_window_device
+        compute_window = kirchhoff_window_device
     if world is None:
         world = dist.get_world_size(group) if dist.is_initialized() else 1
     if rank is None:
         rank = dist.get_rank(group) if dist.is_initialized() else 0
     S, T = x.shape
+    ranges = kirchhoff_output_ranges(T, world, travel_time_us, dist_km, vel)
+    xb, xe = ranges[rank]
+    if exchange is None:
+        exchange = 'broadcast' if gather is True else 'halo'
+    if exchange not in ('halo', 'broadcast'):
+        raise ValueError("exchange must be 'halo' or 'broadcast'")
+    if exchange == 'halo' and gather is True:
+        raise ValueError("exchange='halo' delivers the image to rank src only: pass gather='src' (or False)")
+    uniform = _spacing_is_uniform(travel_time_us, dist_km, vel)
+    if world > 1 and exchange == 'halo' and compute_window is not None:
+        windows = kirchhoff_input_windows(S, T, ranges, travel_time_us, dist_km, vel, window_fn)
+        nchunks = pipeline_chunks if (uniform and pipeline_chunks > 1) else 1
+        res = _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, world, group, src, ranges,
+                                      windows, nchunks, compute_window, gather)
+        return res if gather else (res, (xb, xe))
     broadcast_done = False
-    if world > 1 and gather and pipeline_chunks > 1 and compute_rows is not None:
-        ranges = kirchhoff_output_ranges(T, world, travel_time_us, dist_km, vel)
+    if world > 1 and gather is True and pipeline_chunks > 1 and compute_rows is not None and uniform:
         out = _kirchhoff_sharded_pipelined(x, travel_time_us, dist_km, vel, nearfield, rank, world, group, src, ranges,
                                            pipeline_chunks, compute_rows)
         if out is not None:
@@ -170,8 +295,6 @@ def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=No
         broadcast_done = True
     if world > 1 and not broadcast_done:
         dist.broadcast(x, src=src, group=group)          # the one exchange step on the input side
-    ranges = kirchhoff_output_ranges(T, world, travel_time_us, dist_km, vel)
-    xb, xe = ranges[rank]
     block = compute(x, travel_time_us, dist_km, vel, nearfield, xb, xe) if xe > xb else \
         torch.empty((S, 0), dtype=x.dtype, device=x.device)
     if not gather:
@@ -189,3 +312,22 @@ def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=No
         if e > b:
             out[:, b:e] = allb[r, :, :e - b]
     return out
+
+
+def kirchhoff_sharded_host(data, snum, tnum, travel_time_us, dist_km, vel, nearfield, rank=None, world=None, group=None,
+                           src=0, pipeline_chunks=4):
+    """Host-to-host form of the sharded migration (what a torchrun script calls with the radargram loaded on rank
+    `src`): `data` is the (snum, tnum) host array on `src` (None elsewhere); returns the float64 migrated image as a
+    host array on `src` (page-locked, like RadarData.migrate's result), None elsewhere."""
+    import torch
+    from . import device
+    if rank == src:
+        x = device.to_device(data)
+    else:
+        x = torch.empty((1, 1), dtype=torch.float32, device="cuda").expand(snum, tnum)   # shape carrier: never read
+    out = kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=rank, world=world, gather='src',
+                                   group=group, src=src, pipeline_chunks=pipeline_chunks)
+    if rank != src:
+        torch.cuda.current_stream().synchronize()
+        return None
+    return device.to_host(out, np.float64)

@@ -151,6 +151,19 @@ int impdar_kirchhoff_rows_f32(const float *data, float *out, int snum, int tnum,
                               const double *tt_s, const double *grad_coef, double vel, int nearfield, int x_begin,
                               int x_end, int s_begin, int s_end, int g_hi, void *workspace, size_t workspace_bytes,
                               void *stream);
+/* Column-window form (the multi-GPU halo exchange): `data` holds only the radargram columns [col0, col0 + ncols)
+ * (row stride ld floats) and `out` has row stride ldo (>= x_end - x_begin; pass the full image + x_begin with ldo = tnum
+ * to write a rank's block straight into its final place - also through a peer-mapped pointer).  Geometry vectors stay
+ * those of the WHOLE radargram, so tables, picks and summation order - and therefore the result - are bit for bit what
+ * impdar_kirchhoff_f32 gives on the whole input.  The window must cover every column the range can read:
+ * impdar_kirchhoff_input_window() returns that interval (range + one aperture each side, by distance and by trace
+ * count).  s_begin / s_end / g_hi as in impdar_kirchhoff_rows_f32; (0, snum, snum) = whole image, any geometry.   */
+int impdar_kirchhoff_input_window(int snum, int tnum, const double *dist_m, const double *tt_s, double vel,
+                                  int x_begin, int x_end, int *col0, int *col1);
+int impdar_kirchhoff_window_f32(const float *data, int col0, int ncols, int ld, float *out, int ldo, int snum,
+                                int tnum, const double *dist_m, const double *tt_s, const double *grad_coef,
+                                double vel, int nearfield, int x_begin, int x_end, int s_begin, int s_end, int g_hi,
+                                void *workspace, size_t workspace_bytes, void *stream);
 /* Host-to-host Kirchhoff with the transfers overlapped (the RadarData.migrate(mtype='kirch') call on a host array):
  * h_data HOST (snum, tnum) floats, h_out HOST (snum, tnum) doubles - page-locked memory makes the copies truly
  * asynchronous.  An output row only reads input rows at or below it (the hyperbola runs downwards in time), so the
@@ -165,11 +178,16 @@ int impdar_kirchhoff_host_pipelined_f64(const float *h_data, double *h_out, int 
  * inside the aperture and pairs that took the float64 exact path.  Counting pairs costs an instruction
  * per pair, so it is off unless enabled.  last_stats synchronises the stream of that call.            */
 int impdar_kirchhoff_enable_stats(int on);
-/* Kernel selection: 0 = automatic (uniform-geometry table kernel when the trace spacing is uniform, the
- * general-geometry kernel otherwise), 1 = always the general kernel, 2 = require the table kernel.
- * impdar_kirchhoff_last_path() tells which one the last call used (1 general, 2 table).              */
+/* Kernel selection (per host thread): 0 = automatic (uniform-geometry table path when the trace spacing is uniform,
+ * the general-geometry kernel otherwise), 1 = always the general kernel, 2 = require the table path (shared-memory
+ * tile kernel for the far-field sum, global-gather table kernel for near field / non-finite input), 3 = table path
+ * with the global-gather kernel only.  impdar_kirchhoff_last_path(): 1 general, 2 table (gather), 3 table (tile). */
 int impdar_kirchhoff_set_mode(int mode);
 int impdar_kirchhoff_last_path(void);
+/* After a table-path call whose last_path is 3 (shared-memory tile kernel launched): *stood_down = 1 when the tile
+ * kernel left the work to the gather kernel (non-finite input, or hyperbola intervals wider than its staging
+ * segments), 0 when it did the work; -1 when the last call did not launch it.  Synchronises that call's stream. */
+int impdar_kirchhoff_last_tile_standdown(int *stood_down);
 int impdar_kirchhoff_last_stats(unsigned long long *pairs, unsigned long long *exact_pairs);
 
 /* Reference prototype, migrationlib/mig_cython.h:11 - HOST pointers, float64, synchronous.  Linking

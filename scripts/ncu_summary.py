@@ -14,7 +14,9 @@ keys = ['Kernel Name', 'gpu__time_duration.sum', 'launch__registers_per_thread',
 for vals in rows[2:]:
     print('-' * 100)
     for i, h in enumerate(hdr):
-        if h in keys or (h.startswith('smsp__warp_issue_stalled') and h.endswith('per_warp_active.pct')) \
+        if h in keys or h.startswith('l1tex__data_pipe_lsu_wavefronts') or h.startswith('l1tex__data_bank_conflicts') \
+                or h.startswith('l1tex__m_xbar2l1tex_read_bytes') or h.startswith('lts__t_sectors_srcunit_tex_op_read.sum') \
+                or (h.startswith('smsp__warp_issue_stalled') and h.endswith('per_warp_active.pct')) \
                 or h.startswith('smsp__average_warps_issue_stalled') and h.endswith('_per_issue_active.ratio'):
             try:
                 v = float(vals[i].replace(',', ''))
@@ -36,6 +38,19 @@ if len(sys.argv) > 2:
             continue
         def val(h, table):
             return float(vals[col[h]].replace(',', '')) * table.get(units[col[h]], 1.0)
+        pipes = {}
+        for h in hdr:
+            if h in ('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+                     'l1tex__data_pipe_lsu_wavefronts.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+                     'smsp__issue_active.avg.pct_of_peak_sustained_active', 'l1tex__t_sector_hit_rate.pct',
+                     'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+                     'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+                     'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum'):
+                try:
+                    pipes[h] = float(vals[col[h]].replace(',', ''))
+                except ValueError:
+                    pass
         tr[m.group(1)] = {'dram_bytes': val('dram__bytes_read.sum', mult) + val('dram__bytes_write.sum', mult),
-                          'ncu_ms': val('gpu__time_duration.sum', tmul), 'source': os.path.basename(sys.argv[1])}
+                          'ncu_ms': val('gpu__time_duration.sum', tmul), 'source': os.path.basename(sys.argv[1]),
+                          'pipes': pipes}
     json.dump(tr, open(path, 'w'), indent=1, sort_keys=True)

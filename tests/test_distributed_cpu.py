@@ -64,8 +64,48 @@ def _worker(rank, world, port, q):
     out3 = parallel.kirchhoff_sharded_device(x3, tt, dk, 1.69e8, False, rank=rank, world=world, compute=compute,
                                              compute_rows=irregular, pipeline_chunks=4)
     err = max(err, float(np.linalg.norm(out3.numpy() - ref) / np.linalg.norm(ref)))
+    # the halo exchange: every rank receives only its window of input columns; the injected column-window compute
+    # asserts that it never sees more, poisons what the row chunk may not read, and the image lands on rank 0 only
+    S2, T2 = 40, 400
+    tt2 = np.arange(S2) * 0.01
+    dk2 = np.arange(T2) * 0.0005                      # 0.5 m spacing: aperture = 68 traces << T2
+    full2 = np.random.default_rng(5).standard_normal((S2, T2)).astype(np.float32)
+    ref2 = om.kirchhoff(full2.astype(np.float64), tt2, dk2, 1.69e8, False)
+    reach = 1.69e8 * tt2.max() * 1e-6 / 2.0
+
+    def window_fn(snum, tt_, dk_, vel, xb, xe):
+        d = np.asarray(dk_) * 1e3
+        return (int(np.searchsorted(d, d[xb] - reach * 1.0001 - 1e-9, side='left')),
+                int(np.searchsorted(d, d[xe - 1] + reach * 1.0001 + 1e-9, side='right')))
+
+    wcalls = []
+
+    def compute_window(win, c0, tnum, tt_, dk_, vel, nf, xb, xe, out_block, rows):
+        r0, r1, g_hi = rows
+        wcalls.append((c0, win.shape[1], r0, r1, g_hi))
+        assert tnum == T2 and win.shape[1] < T2        # a window, not the image
+        src_img = np.zeros((S2, T2))
+        src_img[:, c0:c0 + win.shape[1]] = win.numpy().astype(np.float64)
+        src_img[:max(r0 - 1, 0)] = 1e30                # rows this chunk may not read
+        src_img[:, :c0] = 1e30                         # columns outside the window: must not matter
+        src_img[:, c0 + win.shape[1]:] = 1e30
+        out_block[r0:r1] = torch.from_numpy(om.kirchhoff(src_img, tt_, dk_, vel, nf, xb, xe)[r0:r1].astype(np.float32))
+
+    x4 = torch.from_numpy(full2.copy()) if rank == 0 else torch.empty((1, 1)).expand(S2, T2)
+    out4 = parallel.kirchhoff_sharded_device(x4, tt2, dk2, 1.69e8, False, rank=rank, world=world, gather='src',
+                                             compute=compute, compute_window=compute_window, window_fn=window_fn,
+                                             pipeline_chunks=3)
+    if rank == 0:
+        err = max(err, float(np.linalg.norm(out4.numpy() - ref2) / np.linalg.norm(ref2)))
+    else:
+        assert out4 is None
+    assert [c[2:4] for c in wcalls] == list(reversed(parallel.row_chunks(S2, 3)))
+    blk4, rng4 = parallel.kirchhoff_sharded_device(x4, tt2, dk2, 1.69e8, False, rank=rank, world=world, gather=False,
+                                                   compute=compute, compute_window=compute_window, window_fn=window_fn,
+                                                   pipeline_chunks=1)
+    err = max(err, float(np.linalg.norm(blk4.numpy() - ref2[:, rng4[0]:rng4[1]]) / np.linalg.norm(ref2)))
     block, rng_ = parallel.kirchhoff_sharded_device(x, tt, dk, 1.69e8, False, rank=rank, world=world,
-                                                    compute=compute, gather=False)
+                                                    compute=compute, gather=False, exchange='broadcast')
     q.put((rank, err, tuple(block.shape), rng_))
     dist.destroy_process_group()
 

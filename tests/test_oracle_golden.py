@@ -145,3 +145,33 @@ def test_denoise_median(name):
     g = load_golden(name)
     out = of.median_filter(g["data"], int(g["vert_win"]), int(g["hor_win"]))
     assert out.dtype == g["out"].dtype == g["data"].dtype and np.array_equal(out, g["out"])
+
+
+def test_sparse_and_trace_oracles_equal_the_full_ones():
+    """The large-shape variants (selected output samples / traces) restate the same arithmetic as the full-image
+    functions that the golden vectors pin."""
+    from oracle import migration as om
+    rng = np.random.default_rng(0)
+    S, T = 150, 260
+    x = rng.standard_normal((S, T)).astype(np.float32)
+    tt, dk = 0.05 + np.arange(S) * 0.01, np.arange(T) * 0.002
+    for nf in (False, True):
+        full = om.kirchhoff(x.astype(np.float64), tt, dk, 1.69e8, nf)
+        rows = np.array([0, 3, 77, S - 1])
+        traces = [0, 1, 130, T - 1]
+        part = om.kirchhoff_sparse(x, tt, dk, 1.69e8, nf, traces, rows)
+        assert np.max(np.abs(part - full[rows][:, traces])) <= 1e-13 * np.max(np.abs(full))
+    xn = x.copy()
+    xn[40:60, 100:120] = np.nan
+    full = om.kirchhoff(xn.astype(np.float64), tt, dk, 1.69e8, True)
+    part = om.kirchhoff_sparse(xn, tt, dk, 1.69e8, True, [90, 110, 140])
+    assert np.array_equal(np.isnan(part), np.isnan(full[:, [90, 110, 140]]))
+    assert np.nanmax(np.abs(part - full[:, [90, 110, 140]])) <= 1e-13 * np.nanmax(np.abs(full))
+    for (S, T) in ((64, 96), (65, 50)):
+        x = rng.standard_normal((S, T)).astype(np.float32)
+        ti, dk = np.ones(T) * 5.0, np.arange(T) * 0.005
+        _, full = om.stolt(x.astype(np.float64), 1e-8, ti, dk, 1.68e8, 10, 7)
+        tr = [0, 1, T // 2, T - 1]
+        part = om.stolt_traces(x, 1e-8, ti, dk, 1.68e8, 10, 7, traces=tr, row_chunk=13)
+        assert part.shape == (full.shape[0], 4)
+        assert np.max(np.abs(part - full[:, tr])) <= 1e-13 * np.max(np.abs(full))
