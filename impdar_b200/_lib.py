@@ -23,6 +23,7 @@ PROTOTYPES = {
     "impdar_b200_kernel_timer": (_c_int, [_c_int]),
     "impdar_b200_kernel_timer_read": (_c_int, [ctypes.c_char_p, _vp, _vp]),
     "impdar_taper_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_int, _vp]),
+    "impdar_taper_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _vp]),
     "impdar_hfilt_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
     "impdar_hfilt_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
     "impdar_ahfilt_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int]),

@@ -49,6 +49,18 @@ __global__ void __launch_bounds__(256) taper_kernel(const float *__restrict__ x,
     }
 }
 
+// float64 radargrams (the time-wavenumber stub multiplies a float64 array in place, mig_python.py:330-335): one rounding
+// per product in the reference's own order, data * (H * V)
+__global__ void __launch_bounds__(256) taper_f64_kernel(const double *__restrict__ x, double *__restrict__ y, int S, int T,
+                                                        long long rows, double htaper, double vtaper) {
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const double v = taper_weight((int)(row % S), S, vtaper);
+        const double *xr = x + row * (long long)T;
+        double *yr = y + row * (long long)T;
+        for (int c = threadIdx.x; c < T; c += blockDim.x) yr[c] = __dmul_rn(xr[c], __dmul_rn(taper_weight(c, T, htaper), v));
+    }
+}
+
 // -------------------------------------------------------------------------------------------- hfilt
 template <typename T>
 struct Vec4;
@@ -375,6 +387,179 @@ __global__ void __launch_bounds__(256) ahfilt_strip_kernel(const T *__restrict__
                         else f += cj * (double)ring[(q % 7) * W + c];
                     }
                     ys[i] = (T)((double)xs[i] - f * tp);
+                }
+            }
+        }
+    }
+}
+
+// Fast strip kernel (float radargrams with tnum % 4 == 0 - every BASELINE shape; the default).  Same decomposition as
+// ahfilt_strip_kernel - strip of W output traces x chunk of R rows per CTA, float64 prefix sums of the row segment the
+// strip's windows cover, ring of the last seven mean rows, one read and one write of the data - rebuilt around the
+// instruction count, which is what bounded the first version (131 thread-instructions per sample, 56 % issue
+// utilisation, profiles/r01g_ncu_full_ahfilt.txt):
+//   * a thread owns 16 CONTIGUOUS segment elements, loaded as four aligned float4 straight into registers (the segment
+//     start is rounded down to a multiple of 4), scanned in registers, and written once to shared memory as the finished
+//     exclusive prefix (offset folded in) - no staging round trip, no second pass over the prefix buffer;
+//   * the window of every output column is row-invariant: its two padded prefix indices and 1 / width are computed once
+//     per CTA and kept in registers, so a window mean is two LDS.64, a DSUB and a DMUL - no per-element window logic;
+//   * a thread owns PAIRS of adjacent output columns: ring rows, x and y move as float2 and the 7-tap combination runs
+//     on the packed fp32x2 pipe.
+constexpr int AHF_E = 16;                 // segment elements per thread
+constexpr int AHF_NMAX = 256 * AHF_E;     // longest row segment (strip + window halo)
+constexpr int AHF_PAIRS = 4;              // column pairs per thread -> strips of up to 2048 output traces
+__device__ __forceinline__ int ahf_pad(int k) { return k + (k >> 4); }   // 17-double pitch per thread: conflict-free
+
+__global__ void __launch_bounds__(256, 2) ahfilt_fast_kernel(const float *__restrict__ x, float *__restrict__ y, int S,
+                                                             int Tn, int w, int tail_lo,
+                                                             const double *__restrict__ taper, int W, int R) {
+    extern __shared__ double smem_d[];
+    double *Q = smem_d;                                   // exclusive prefix: Q[ahf_pad(k)] = sum of segment elements < k
+    double *wtot = Q + (AHF_NMAX + AHF_NMAX / 16 + 8);    // [8]
+    float *ring = reinterpret_cast<float *>(wtot + 8);    // [7][W]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = blockIdx.x * W, c1 = min(Tn, c0 + W);
+    const float *xb = x + (long long)blockIdx.z * S * Tn;
+    float *yb = y + (long long)blockIdx.z * S * Tn;
+    const int h = w / 2;
+    int L0, L1;
+    {
+        int lo, hi;
+        ahfilt_window(c0, Tn, w, tail_lo, lo, hi);
+        L0 = lo;
+        L1 = hi;
+        ahfilt_window(c1 - 1, Tn, w, tail_lo, lo, hi);
+        L0 = min(L0, lo);
+        L1 = max(L1, hi);
+        if (c1 - 1 >= Tn - h) {
+            L0 = min(L0, tail_lo);
+            L1 = Tn;
+        }
+    }
+    L0 &= ~3;                                             // aligned float4 loads (tnum % 4 == 0, 16-byte aligned rows)
+    const int s_begin = blockIdx.y * R, s_end = min(S, s_begin + R);
+    const int r0 = max(0, s_begin - 3), r1 = min(S - 1, s_end + 2);
+    int next_out = s_begin;
+
+    // row-invariant window constants of this thread's eight output columns
+    int ia[2 * AHF_PAIRS], ie[2 * AHF_PAIRS];
+    double inv[2 * AHF_PAIRS];
+#pragma unroll
+    for (int u = 0; u < 2 * AHF_PAIRS; ++u) {
+        const int i = c0 + 2 * tid + 512 * (u >> 1) + (u & 1);
+        int lo = L0, hi = L0;
+        if (i < c1) ahfilt_window(i, Tn, w, tail_lo, lo, hi);
+        ia[u] = ahf_pad(lo - L0);
+        ie[u] = ahf_pad(hi - L0);
+        inv[u] = 1.0 / (double)(hi - lo);   // inf for an empty window: 0 * inf = NaN like np.mean of an empty slice
+    }
+    // software pipeline: the row segment of iteration r + 1 and the centre row of this iteration's output are in flight
+    // while row r is scanned
+    const int kb = AHF_E * tid;             // this thread's first segment element
+    float4 nxt[AHF_E / 4];
+    auto load_segment = [&](int r) {
+        const float *xr = xb + (long long)r * Tn + L0 + kb;
+#pragma unroll
+        for (int v4 = 0; v4 < AHF_E / 4; ++v4)
+            nxt[v4] = (L0 + kb + 4 * v4 < Tn) ? *reinterpret_cast<const float4 *>(xr + 4 * v4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    load_segment(r0);
+    if (tid == 0) Q[0] = 0.0;
+    for (int r = r0; r <= r1; ++r) {
+        // ---- thread-local inclusive scan of 16 contiguous elements, in float64 registers
+        double v[AHF_E];
+        double run = 0.0;
+#pragma unroll
+        for (int v4 = 0; v4 < AHF_E / 4; ++v4) {
+            run += (double)nxt[v4].x; v[4 * v4 + 0] = run;
+            run += (double)nxt[v4].y; v[4 * v4 + 1] = run;
+            run += (double)nxt[v4].z; v[4 * v4 + 2] = run;
+            run += (double)nxt[v4].w; v[4 * v4 + 3] = run;
+        }
+        if (r < r1) load_segment(r + 1);
+        float2 xc[AHF_PAIRS];
+        {
+            const float *xs = xb + (long long)min(next_out, S - 1) * Tn + c0 + 2 * tid;
+#pragma unroll
+            for (int u = 0; u < AHF_PAIRS; ++u)
+                xc[u] = (c0 + 2 * tid + 512 * u < c1) ? *reinterpret_cast<const float2 *>(xs + 512 * u) : make_float2(0.f, 0.f);
+        }
+        // ---- exclusive offset of this thread's chunk: warp scan of the chunk totals, then the warp totals
+        double inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+        }
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();                     // also: the previous row's window reads of Q and ring reads are done
+        double off = inc - run;
+        for (int u = 0; u < warp; ++u) off += wtot[u];
+        {
+            double *qc = Q + 17 * tid + 1;   // ahf_pad(16 tid + 1 + e) = 17 tid + 1 + e for e < 15, + 1 more for e = 15
+#pragma unroll
+            for (int e = 0; e < AHF_E - 1; ++e) qc[e] = off + v[e];
+            qc[AHF_E] = off + v[AHF_E - 1];
+        }
+        __syncthreads();
+        // ---- window means of this thread's column pairs into the ring
+        float *mrow = ring + (r % 7) * W + 2 * tid;
+#pragma unroll
+        for (int u = 0; u < AHF_PAIRS; ++u) {
+            if (c0 + 2 * tid + 512 * u < c1) {
+                const float m0 = (float)((Q[ie[2 * u]] - Q[ia[2 * u]]) * inv[2 * u]);
+                const float m1 = (float)((Q[ie[2 * u + 1]] - Q[ia[2 * u + 1]]) * inv[2 * u + 1]);
+                *reinterpret_cast<float2 *>(mrow + 512 * u) = make_float2(m0, m1);
+            }
+        }
+        __syncthreads();
+        bool first_emit = true;
+        while (next_out < s_end && (next_out + 3 <= r || r == S - 1)) {
+            const int s = next_out++;
+            const bool have_xc = first_emit;  // xc holds row s only for the first row emitted in this iteration
+            first_emit = false;
+            const double tp = taper[s];
+            const float *xs = xb + (long long)s * Tn;
+            float *ys = yb + (long long)s * Tn;
+            if (s >= 3 && s + 3 < S) {
+                // interior: the 7-tap triangular kernel [1 2 3 4 3 2 1] / 16 on rows s-3 .. s+3, two columns at a time
+                const float *q0 = ring + ((s + 4) % 7) * W + 2 * tid, *q1 = ring + ((s + 5) % 7) * W + 2 * tid;
+                const float *q2 = ring + ((s + 6) % 7) * W + 2 * tid, *q3 = ring + (s % 7) * W + 2 * tid;
+                const float *q4 = ring + ((s + 1) % 7) * W + 2 * tid, *q5 = ring + ((s + 2) % 7) * W + 2 * tid;
+                const float *q6 = ring + ((s + 3) % 7) * W + 2 * tid;
+                const float tpf = (float)tp;
+                const float2 ntp = make_float2(-tpf, -tpf);
+#pragma unroll
+                for (int u = 0; u < AHF_PAIRS; ++u) {
+                    const int i = c0 + 2 * tid + 512 * u;
+                    if (i < c1) {
+                        const int o = 512 * u;
+                        const float2 a06 = __fadd2_rn(*reinterpret_cast<const float2 *>(q0 + o), *reinterpret_cast<const float2 *>(q6 + o));
+                        const float2 a15 = __fadd2_rn(*reinterpret_cast<const float2 *>(q1 + o), *reinterpret_cast<const float2 *>(q5 + o));
+                        const float2 a24 = __fadd2_rn(*reinterpret_cast<const float2 *>(q2 + o), *reinterpret_cast<const float2 *>(q4 + o));
+                        float2 f = __fmul2_rn(make_float2(0.0625f, 0.0625f), a06);
+                        f = __ffma2_rn(make_float2(0.125f, 0.125f), a15, f);
+                        f = __ffma2_rn(make_float2(0.1875f, 0.1875f), a24, f);
+                        f = __ffma2_rn(make_float2(0.25f, 0.25f), *reinterpret_cast<const float2 *>(q3 + o), f);
+                        const float2 xv = have_xc ? xc[u] : *reinterpret_cast<const float2 *>(xs + i);
+                        *reinterpret_cast<float2 *>(ys + i) = __ffma2_rn(f, ntp, xv);       // x - f * taper
+                    }
+                }
+            } else {
+                // edges: the kernel on the odd-extended mean trace, folded onto real rows
+                for (int i = c0 + tid; i < c1; i += 256) {
+                    const int c = i - c0;
+                    double f = 0.0;
+#pragma unroll
+                    for (int j = -3; j <= 3; ++j) {
+                        const double cj = (double)(4 - (j < 0 ? -j : j)) / 16.0;
+                        const int q = s + j;
+                        if (q < 0) f += cj * (2.0 * (double)ring[c] - (double)ring[((-q) % 7) * W + c]);
+                        else if (q >= S) f += cj * (2.0 * (double)ring[((S - 1) % 7) * W + c] -
+                                                    (double)ring[((2 * (S - 1) - q) % 7) * W + c]);
+                        else f += cj * (double)ring[(q % 7) * W + c];
+                    }
+                    ys[i] = (float)((double)xs[i] - f * tp);
                 }
             }
         }
@@ -778,7 +963,7 @@ static int hfilt_impl(const T *x, T *y, int S, int Tn, int batch, int htr1, int 
 }
 
 static const size_t AHFILT_SMEM_LIMIT = 200 * 1024;
-static int g_ahfilt_force_rowwise = 0;  // testing hook: 0 = auto (strip kernel, else warp-sliding), 1 = one-row-per-CTA kernel, 3 = warp-sliding kernel
+static int g_ahfilt_force_rowwise = 0;  // testing hook: 0 = auto (fast strip kernel, strip kernel, else warp-sliding), 1 = one-row-per-CTA kernel, 2 = first strip kernel, 3 = warp-sliding kernel
 
 template <typename T>
 static int ahfilt_impl(const T *x, T *y, int S, int Tn, int batch, int w, const double *taper, void *ws,
@@ -831,6 +1016,29 @@ static int ahfilt_impl(const T *x, T *y, int S, int Tn, int batch, int w, const 
             if (L1 - L0 > nmax) nmax = L1 - L0;
         }
         const size_t smem_strip = (size_t)(4096 + 256 + 256 + 8) * sizeof(double) + (size_t)7 * W * sizeof(T);
+        if (sizeof(T) == 4 && g_ahfilt_force_rowwise == 0 && (Tn & 3) == 0 && (W & 1) == 0 && nmax + 3 <= AHF_NMAX &&
+            ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0) {
+            int dev = 0;
+            IMPDAR_CUDA(cudaGetDevice(&dev));
+            static bool fast_attr[64];
+            const size_t smem_fast = (size_t)(AHF_NMAX + AHF_NMAX / 16 + 8 + 8) * sizeof(double) + (size_t)7 * W * sizeof(float);
+            if (dev >= 0 && dev < 64 && !fast_attr[dev]) {
+                IMPDAR_CUDA(cudaFuncSetAttribute(ahfilt_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                fast_attr[dev] = true;
+            }
+            int R = 64;
+            auto ctas = [&](int r) { return (long long)batch * ((S + r - 1) / r) * ((Tn + W - 1) / W); };
+            if (ctas(R) < (long long)num_sms() * 4) R = 32;      // single profiles: more row chunks, 3 + 3 halo rows each
+            if (const char *e = getenv("IMPDAR_AH_R")) R = atoi(e);   // development A/B switch
+            dim3 grid((Tn + W - 1) / W, (S + R - 1) / R, batch);
+            IMPDAR_CHECK_ARG(batch <= 65535 && grid.y <= 65535, "ahfilt: batch too large");
+            ktimer_begin("ahfilt_fast_kernel", (cudaStream_t)stream);
+            ahfilt_fast_kernel<<<grid, 256, smem_fast, (cudaStream_t)stream>>>((const float *)x, (float *)y, S, Tn, w, tail_lo,
+                                                                                 taper, W, R);
+            ktimer_end((cudaStream_t)stream);
+            IMPDAR_LAUNCH_CHECK();
+            return IMPDAR_B200_OK;
+        }
         if (nmax <= 4096) {
             static bool attr_done = false;
             if (!attr_done) {
@@ -894,6 +1102,18 @@ int impdar_taper_f32(const float *x, float *y, int S, int T, int batch, double h
     return IMPDAR_B200_OK;
 }
 
+int impdar_taper_f64(const double *x, double *y, int S, int T, int batch, double htaper, double vtaper, void *stream) {
+    IMPDAR_CHECK_ARG(x && y, "taper: null pointer");
+    IMPDAR_CHECK_ARG(S > 0 && T > 0 && batch > 0, "taper: bad shape");
+    const long long rows = (long long)batch * S;
+    long long grid = rows;
+    const long long cap = (long long)num_sms() * 32;
+    if (grid > cap) grid = cap;
+    taper_f64_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, y, S, T, rows, htaper, vtaper);
+    IMPDAR_LAUNCH_CHECK();
+    return IMPDAR_B200_OK;
+}
+
 int impdar_hfilt_f32(const float *x, float *y, int S, int T, int batch, int htr1, int htrn,
                      const double *taper, int trunc_avg, void *stream) {
     return hfilt_impl<float>(x, y, S, T, batch, htr1, htrn, taper, trunc_avg, stream);
@@ -911,7 +1131,7 @@ size_t impdar_ahfilt_workspace_bytes(int S, int T, int batch) {
     return (size_t)num_sms() * 4 * (size_t)(T + 1) * sizeof(double);
 }
 int impdar_ahfilt_force_rowwise(int on) {
-    g_ahfilt_force_rowwise = (on == 3) ? 3 : (on ? 1 : 0);
+    g_ahfilt_force_rowwise = (on >= 0 && on <= 3) ? on : 1;
     return IMPDAR_B200_OK;
 }
 int impdar_ahfilt_f32(const float *x, float *y, int S, int T, int batch, int w, const double *taper, void *ws,

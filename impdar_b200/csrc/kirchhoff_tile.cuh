@@ -11,26 +11,57 @@
 // serve every (row, m) of the block that picks row k: each pair is one conflict-free shared-memory read (any
 // alignment is one wavefront), L2 traffic drops from ~2 B to ~0.7 B per pair.
 //
-// Summation order per output sample: m ascending, partial sums flushed into a second accumulator at the end of every
-// stage; stages are windows of KT_W source rows at ABSOLUTE multiples of KT_W, so the order - and therefore the
-// result, bit for bit - does not depend on how the image is cut into row chunks, trace ranges or CTAs.
+// Summation order per output sample: m ascending, partial sums flushed into a second accumulator after every
+// KT_FLUSH-th stage; stages are windows of KT_W source rows at ABSOLUTE multiples of KT_W (and the flushes at absolute
+// window indices), so the order - and therefore the result, bit for bit - does not depend on how the image is cut
+// into row chunks, trace ranges or CTAs.
 #pragma once
 
 namespace impdar {
 
-constexpr int KT_NW = 16;            // consumer warps per CTA
-constexpr int KT_RW = 2;             // output rows per consumer warp
+// tunables (A/B builds: python -m impdar_b200._build -DKT_CFG_NW=16 -DKT_CFG_RW=2 --out=...)
+#ifndef KT_CFG_NW
+#define KT_CFG_NW 28
+#endif
+#ifndef KT_CFG_NP
+#define KT_CFG_NP 4
+#endif
+#ifndef KT_CFG_RW
+#define KT_CFG_RW 1
+#endif
+#ifndef KT_CFG_TR
+#define KT_CFG_TR 8
+#endif
+#ifndef KT_CFG_W
+#define KT_CFG_W 16
+#endif
+#ifndef KT_CFG_NST
+#define KT_CFG_NST 4
+#endif
+constexpr int KT_NW = KT_CFG_NW;     // consumer warps per CTA
+constexpr int KT_NP = KT_CFG_NP;     // producer warps per CTA (KT_NW + KT_NP <= 32).  cp.async.bulk is a warp-uniform
+                                     // instruction: the rows of a stage are issued one after the other (~9 issue slots
+                                     // and a few R2UR round trips each), so ONE producer warp feeding 32 copies per stage
+                                     // was the kernel's bottleneck (ncu r02c: consumers spun 56 times per stage wait)
+constexpr int KT_RW = KT_CFG_RW;     // output rows per consumer warp
 constexpr int KT_Q = KT_NW * KT_RW;  // output rows per CTA
-constexpr int KT_TR = 8;             // output traces per lane (stride 32)
+constexpr int KT_TR = KT_CFG_TR;     // output traces per lane (stride 32), even
 constexpr int KT_X = 32 * KT_TR;     // output traces per CTA
-constexpr int KT_W = 16;             // source rows per stage (<= 32: one producer lane per row)
-constexpr int KT_NST = 4;            // stages in the ring
+constexpr int KT_W = KT_CFG_W;       // source rows per stage (<= 32: one producer lane per row)
+constexpr int KT_NST = KT_CFG_NST;   // stages in the ring
+#ifndef KT_CFG_FLUSH
+#define KT_CFG_FLUSH 4
+#endif
+constexpr int KT_FLUSH = KT_CFG_FLUSH;           // stages (absolute index) between second-level accumulator flushes; power of two
 constexpr int KT_SPAN = 120;         // widest [mlo, mhi] interval the staged segments hold
 constexpr int KT_SEGW = KT_X + KT_SPAN + 8;                   // floats per staged segment (alignment shift <= 3)
 constexpr int KT_STAGE_FLOATS = KT_W * 2 * KT_SEGW;
+constexpr int KT_RING = 64;           // table entries per (warp, row) ring: two chunks of 32
 constexpr size_t KT_SMEM = (size_t)KT_NST * KT_STAGE_FLOATS * sizeof(float) + KT_NST * KT_W * sizeof(int2) +
-                           2 * KT_NST * sizeof(unsigned long long) + 16;
-constexpr int KT_THREADS = (KT_NW + 1) * 32;
+                           (size_t)KT_NW * KT_RW * KT_RING * sizeof(int2) + 2 * KT_NST * sizeof(unsigned long long) + 16;
+constexpr int KT_THREADS = (KT_NW + KT_NP) * 32;
+constexpr int KT_RPP = (KT_W + KT_NP - 1) / KT_NP;   // stage rows per producer warp
+static_assert(KT_RPP <= 32 && KT_NW + KT_NP <= 32, "tile kernel configuration");
 
 struct KirchTileParams {
     const int2 *seg;     // [nblocks][S]: {mlo, mhi} per source row (mlo > mhi: not used by the block)
@@ -48,19 +79,26 @@ __device__ __forceinline__ void kt_mbar_arrive(unsigned long long *bar) {
 __device__ __forceinline__ void kt_mbar_arrive_tx(unsigned long long *bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(kt_smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void kt_mbar_wait(unsigned long long *bar, unsigned parity) {
-    const unsigned sb = kt_smem_u32(bar);
+#ifndef KT_CFG_SLEEP
+#define KT_CFG_SLEEP 0
+#endif
+__device__ __forceinline__ bool kt_mbar_try(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "KT_WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra KT_WAIT_DONE;\n"
-        "bra KT_WAIT_LOOP;\n"
-        "KT_WAIT_DONE:\n"
-        "}\n" ::"r"(sb),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(kt_smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void kt_mbar_wait(unsigned long long *bar, unsigned parity) {
+    while (!kt_mbar_try(bar, parity)) {
+        if (KT_CFG_SLEEP) __nanosleep(KT_CFG_SLEEP);   // a waiting warp leaves the issue slots to the working ones
+    }
 }
 __device__ __forceinline__ void kt_bulk_load(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -135,7 +173,8 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kirch_tile_kernel(const __grid_
     if (q.sched_flags[0] != 0 || p.flags[0] != 0) return;   // wide intervals or non-finite input: the table kernel runs
     float *buf = reinterpret_cast<float *>(kt_smem_raw);
     int2 *hdr = reinterpret_cast<int2 *>(buf + (size_t)KT_NST * KT_STAGE_FLOATS);
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(hdr + KT_NST * KT_W);
+    int2 *rings = hdr + KT_NST * KT_W;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(rings + KT_NW * KT_RW * KT_RING);
     unsigned long long *empty = full + KT_NST;
 
     const int b = blockIdx.x;                       // row block (fast index: concurrent CTAs share the column window in L2)
@@ -147,15 +186,16 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kirch_tile_kernel(const __grid_
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < KT_NST; ++i) {
-            kt_mbar_init(&full[i], 1);
+            kt_mbar_init(&full[i], KT_NP);
             kt_mbar_init(&empty[i], KT_NW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == KT_NW) {
-        // ---------------------------------------------------------------- producer: one lane per source row of the stage
+    if (warp >= KT_NW) {
+        // ------------------------------------------------- producers: warp pw issues rows [pw KT_RPP, (pw + 1) KT_RPP) of a stage
+        const int pw = warp - KT_NW;
         const int2 *__restrict__ sb = q.seg + (size_t)b * p.S;
         for (int s = 0; s < nst; ++s) {
             const int slot = s % KT_NST;
@@ -164,8 +204,9 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kirch_tile_kernel(const __grid_
             unsigned bytes = 0, nl = 0, nr = 0;
             const float *gl = nullptr, *gr = nullptr;
             float *dl = nullptr, *dr = nullptr;
-            if (lane < KT_W) {
-                const int k = kbase + s * KT_W + lane;
+            const int j = pw * KT_RPP + lane;                // row of the stage
+            if (lane < KT_RPP && j < KT_W) {
+                const int k = kbase + s * KT_W + j;
                 int2 e = make_int2(1, 0);
                 if (k >= t0 && k < p.S) e = sb[k];
                 if (e.y >= e.x) {
@@ -177,10 +218,10 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kirch_tile_kernel(const __grid_
                     nr = (unsigned)((shr + KT_X + span + 3) & ~3);
                     gl = p.gP + (il - shl);
                     gr = p.gP + (ir - shr);
-                    dl = sbuf + (size_t)lane * 2 * KT_SEGW;
+                    dl = sbuf + (size_t)j * 2 * KT_SEGW;
                     dr = dl + KT_SEGW;
-                    // value of output trace x0 + j at offset m: left  buf[offL + j - m], right buf[offR + j + m]
-                    hdr[slot * KT_W + lane] = make_int2((int)(dl - buf) + shl + e.y, (int)(dr - buf) + shr - e.x);
+                    // value of output trace x0 + i at offset m: left  buf[offL + i - m], right buf[offR + i + m]
+                    hdr[slot * KT_W + j] = make_int2((int)(dl - buf) + shl + e.y, (int)(dr - buf) + shr - e.x);
                     bytes = (nl + nr) * 4u;
                 }
             }
@@ -197,9 +238,16 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kirch_tile_kernel(const __grid_
     }
 
     // -------------------------------------------------------------------- consumers: warp = KT_RW output rows x KT_X traces
-    float acc[KT_RW][KT_TR], tot[KT_RW][KT_TR];
-    int mcur[KT_RW], mend[KT_RW];
+    // accumulators as fp32x2 pairs: the adds and FMAs issue on the packed pipe (half the instructions, same roundings)
+    float2 acc[KT_RW][KT_TR / 2], tot[KT_RW][KT_TR / 2];
+    // The table row of an output sample is walked once, front to back.  It is fetched 32 entries at a time with one
+    // coalesced load per lane, a chunk ahead of its use, and parked in a warp-private shared-memory ring, so the walk
+    // itself never waits on global memory (the L1 left beside 200 KB of staging buffers does not hold 31 table rows).
+    int mcur[KT_RW], mend[KT_RW], cready[KT_RW];
     const int2 *trow[KT_RW];
+    int2 pre[KT_RW];
+    int2 *ring[KT_RW];
+    const int2 sentinel = make_int2(0x7fffffff, 0);
 #pragma unroll
     for (int w = 0; w < KT_RW; ++w) {
         const int ti = t0 + warp + w * KT_NW;
@@ -207,13 +255,16 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kirch_tile_kernel(const __grid_
         mcur[w] = 0;
         mend[w] = live ? p.nm[ti] : 0;
         trow[w] = p.tab + (size_t)(live ? ti : t0) * p.A1;
+        ring[w] = rings + (size_t)(warp * KT_RW + w) * KT_RING;
+        ring[w][lane] = lane < mend[w] ? __ldg(trow[w] + lane) : sentinel;              // chunk 0
+        pre[w] = 32 + lane < mend[w] ? __ldg(trow[w] + 32 + lane) : sentinel;            // chunk 1, parked when chunk 0 is entered
+        cready[w] = 0;
 #pragma unroll
-        for (int r = 0; r < KT_TR; ++r) acc[w][r] = tot[w][r] = 0.f;
+        for (int r = 0; r < KT_TR / 2; ++r) acc[w][r] = tot[w][r] = make_float2(0.f, 0.f);
     }
+    __syncwarp();
     const float *__restrict__ lbuf = buf + lane;
-    int2 ecur[KT_RW];
-#pragma unroll
-    for (int w = 0; w < KT_RW; ++w) ecur[w] = mend[w] > 0 ? __ldg(trow[w]) : make_int2(0x7fffffff, 0);
+    const int sabs0 = kbase / KT_W;                 // absolute index of this block's first stage window
     for (int s = 0; s < nst; ++s) {
         const int slot = s % KT_NST;
         kt_mbar_wait(&full[slot], (unsigned)((s / KT_NST) & 1));
@@ -222,37 +273,43 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kirch_tile_kernel(const __grid_
 #pragma unroll
         for (int w = 0; w < KT_RW; ++w) {
             int m = mcur[w];
-            const int n1 = mend[w] - 1;
-            const int2 *__restrict__ tp = trow[w];
-            int2 e = ecur[w];
-            while (e.x < kend) {                       // the sentinel ends the row
-                ++tp;
-                int2 en = make_int2(0x7fffffff, 0);
-                if (m < n1) en = __ldg(tp);
+            while (true) {
+                const int c = m >> 5;
+                if (c + 1 > cready[w]) {               // entering chunk c: chunk c + 1 goes into the other half of the ring
+                    ring[w][((c + 1) & 1) * 32 + lane] = pre[w];
+                    __syncwarp();
+                    const int nx = (c + 2) * 32 + lane;
+                    pre[w] = nx < mend[w] ? __ldg(trow[w] + nx) : sentinel;
+                    cready[w] = c + 1;
+                }
+                const int2 e = ring[w][m & (KT_RING - 1)];
+                if (e.x >= kend) break;                // next stage, or the sentinel past the end of the row
                 if (e.x >= 0) {
                     const int2 o = h[e.x];
-                    const float wgt = __int_as_float(e.y);
+                    // m == 0: left and right segment hold the same element, w/2 (g + g) == w g exactly
+                    const float wgt = __int_as_float(e.y) * (m == 0 ? 0.5f : 1.0f);
+                    const float2 w2 = make_float2(wgt, wgt);
                     const float *__restrict__ pl = lbuf + (o.x - m);
                     const float *__restrict__ pr = lbuf + (o.y + m);
-                    if (m != 0) {
 #pragma unroll
-                        for (int r = 0; r < KT_TR; ++r) acc[w][r] = fmaf(wgt, pl[32 * r] + pr[32 * r], acc[w][r]);
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < KT_TR; ++r) acc[w][r] = fmaf(wgt, pl[32 * r], acc[w][r]);
+                    for (int r = 0; r < KT_TR / 2; ++r) {
+                        const float2 l = make_float2(pl[64 * r], pl[64 * r + 32]);
+                        const float2 g = make_float2(pr[64 * r], pr[64 * r + 32]);
+                        acc[w][r] = __ffma2_rn(w2, __fadd2_rn(l, g), acc[w][r]);
                     }
                 }
-                e = en;
                 ++m;
             }
             mcur[w] = m;
-            trow[w] = tp;
-            ecur[w] = e;
+        }
+        if (((sabs0 + s) & (KT_FLUSH - 1)) == KT_FLUSH - 1) {     // second-level accumulation at absolute window indices
 #pragma unroll
-            for (int r = 0; r < KT_TR; ++r) {
-                tot[w][r] += acc[w][r];
-                acc[w][r] = 0.f;
-            }
+            for (int w = 0; w < KT_RW; ++w)
+#pragma unroll
+                for (int r = 0; r < KT_TR / 2; ++r) {
+                    tot[w][r] = __fadd2_rn(tot[w][r], acc[w][r]);
+                    acc[w][r] = make_float2(0.f, 0.f);
+                }
         }
         __syncwarp();
         if (lane == 0) kt_mbar_arrive(&empty[slot]);
@@ -262,9 +319,11 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kirch_tile_kernel(const __grid_
         const int ti = t0 + warp + w * KT_NW;
         if (ti >= p.s_end) continue;
 #pragma unroll
-        for (int r = 0; r < KT_TR; ++r) {
-            const int x = x0 + lane + 32 * r;
-            if (x < p.x_end) p.out[(size_t)ti * p.ldo + (x - p.x_begin)] = tot[w][r];
+        for (int r = 0; r < KT_TR / 2; ++r) {
+            const float2 v = __fadd2_rn(tot[w][r], acc[w][r]);
+            const int x = x0 + lane + 64 * r;
+            if (x < p.x_end) p.out[(size_t)ti * p.ldo + (x - p.x_begin)] = v.x;
+            if (x + 32 < p.x_end) p.out[(size_t)ti * p.ldo + (x + 32 - p.x_begin)] = v.y;
         }
     }
 }

@@ -57,14 +57,31 @@ struct PhshParams {
     float inv_s;
 };
 
+// ws = 2.*np.pi*np.fft.fftfreq(nt, d=dt) and kx = 2.*np.pi*np.fft.fftfreq(tnum, d=dx) (:268-269) with numpy's OWN float64
+// operation sequence - fftfreq is `results * (1.0 / (n * d))` on integer results, then one multiply by the double
+// 2*pi - each step rounded on its own.  This matters: the propagating / evanescent decision `vkx2 < w**2.` (:411-412)
+// is an EXACT TIE for whole families of (w, kx) bins on the usual "nice" geometries (dt = 1e-8, dx = 5, v = 1.69e8,
+// power-of-two sizes: v k nt dt / (2 tnum dx) is an integer), and such a bin - phase ~ 0 - adds a tau-independent
+// FK / (snum tnum) to TK, i.e. 1e-3 of relative L2, if it is classified differently from the reference.
+#define PS_TWO_PI 6.283185307179586
 __device__ __forceinline__ double ps_omega(int iw, int nt, double dt) {
-    // 2 pi fftfreq(nt, dt)[iw], with w == 0 replaced by 1e-10/dt (:404-406, :446-448)
+    // with w == 0 replaced by 1e-10/dt (:404-406, :446-448)
     const int fi = (iw < (nt + 1) / 2) ? iw : iw - nt;
     if (fi == 0) return 1e-10 / dt;
-    return 2.0 * 3.14159265358979323846 * (double)fi / ((double)nt * dt);
+    const double val = __ddiv_rn(1.0, __dmul_rn((double)nt, dt));
+    return __dmul_rn(PS_TWO_PI, __dmul_rn((double)fi, val));
 }
 __device__ __forceinline__ double ps_kx(int k, int T, double dx) {
-    return 2.0 * 3.14159265358979323846 * (double)k / ((double)T * dx);  // k <= T/2: the non-negative branch
+    const double val = __ddiv_rn(1.0, __dmul_rn((double)T, dx));
+    return __dmul_rn(PS_TWO_PI, __dmul_rn((double)k, val));  // k <= T/2: the non-negative branch (kx enters squared)
+}
+// (vmig*kx/2.)**2. (:411), w**2., and -phase = w*dt*sqrt(1.0 - vkx2/w**2.) (:415), every operation rounded as numpy does
+__device__ __forceinline__ double ps_vkx2(double vel, double kx) {
+    const double h = __ddiv_rn(__dmul_rn(vel, kx), 2.0);
+    return __dmul_rn(h, h);
+}
+__device__ __forceinline__ double ps_phi(double w, double dt, double vkx2, double w2) {
+    return __dmul_rn(__dmul_rn(w, dt), __dsqrt_rn(__dsub_rn(1.0, __ddiv_rn(vkx2, w2))));
 }
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -100,9 +117,9 @@ __device__ __forceinline__ void ps_commit(const PhshParams &p, float2 (*buf)[PS_
             }
             if (nyq_const && p.nt >= 2) {
                 const double w = ps_omega(p.nt / 2, p.nt, p.dt);
-                const double vk = p.vel * ps_kx(kk, p.T, p.dx) / 2.0;
-                if (vk * vk < w * w) {
-                    const double phi = w * p.dt * sqrt(1.0 - vk * vk / (w * w));
+                const double vkx2n = ps_vkx2(p.vel, ps_kx(kk, p.T, p.dx)), w2n = __dmul_rn(w, w);
+                if (vkx2n < w2n) {
+                    const double phi = ps_phi(w, p.dt, vkx2n, w2n);
                     const float cn = (float)cos((double)(tau + 1) * phi);
                     const float2 f = p.FK[(size_t)(p.nt / 2) * p.K + kk];
                     s.x = fmaf(f.x, cn, s.x);
@@ -137,8 +154,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) phsh_const_kernel(const __grid_
     const int tid = threadIdx.x;
     const int k = blockIdx.x * PSC_COLS + (tid % PSC_COLS);
     const bool kvalid = k < p.K;
-    const double vk = p.vel * ps_kx(kvalid ? k : 0, p.T, p.dx) / 2.0;
-    const double vkx2 = vk * vk;  // (vmig*kx/2)^2   (:411)
+    const double vkx2 = ps_vkx2(p.vel, ps_kx(kvalid ? k : 0, p.T, p.dx));  // (vmig*kx/2)^2   (:411)
 
     for (int ch = 0; ch * PSC_WCHUNK < p.nt; ++ch) {
         float2 z[PSC_PER];
@@ -148,8 +164,9 @@ __global__ void __launch_bounds__(PS_THREADS, 1) phsh_const_kernel(const __grid_
             float2 g = make_float2(0.f, 0.f), zz = make_float2(1.f, 0.f), z64 = zz;
             if (kvalid && iw < p.nt && !(p.nt >= 2 && iw == p.nt / 2)) {  // the Nyquist bin is added at commit
                 const double w = ps_omega(iw, p.nt, p.dt);
-                if (vkx2 < w * w) {  // propagating (:412)
-                    const double phi = w * p.dt * sqrt(1.0 - vkx2 / (w * w));  // = -phase (:415); cp = e^{+i phi}
+                const double w2 = __dmul_rn(w, w);
+                if (vkx2 < w2) {  // propagating (:412)
+                    const double phi = ps_phi(w, p.dt, vkx2, w2);  // = -phase (:415); cp = e^{+i phi}
                     double sn, cs;
                     sincos(phi, &sn, &cs);
                     zz = make_float2((float)cs, (float)sn);
@@ -298,9 +315,9 @@ __device__ __forceinline__ void pp_commit(const PhshParams &p, float2 (*buf)[NW]
             }
             if (nyq_const && p.nt >= 2) {
                 const double w = ps_omega(p.nt / 2, p.nt, p.dt);
-                const double vk = p.vel * ps_kx(k, p.T, p.dx) / 2.0;
-                if (vk * vk < w * w) {
-                    const double phi = w * p.dt * sqrt(1.0 - vk * vk / (w * w));
+                const double vkx2n = ps_vkx2(p.vel, ps_kx(k, p.T, p.dx)), w2n = __dmul_rn(w, w);
+                if (vkx2n < w2n) {
+                    const double phi = ps_phi(w, p.dt, vkx2n, w2n);
                     const float cn = (float)cos((double)(tau + 1) * phi);
                     const float2 f = p.FK[(size_t)(p.nt / 2) * p.K + k];
                     s.x = fmaf(f.x, cn, s.x);
@@ -341,10 +358,11 @@ __global__ void __launch_bounds__(PP_THREADS, 2) phsh_const_pair_kernel(const __
     const int tid = threadIdx.x;
     const int k = blockIdx.x;
     const int nh = max(1, p.nt / 2);  // nt == 1: the single bin w = 0
-    const double vk = p.vel * ps_kx(k, p.T, p.dx) / 2.0;
-    const double vkx2 = vk * vk;  // (vmig*kx/2)^2   (:411)
-    // pairs below s ~ vk nt dt / 2 pi are evanescent for every tau (:412); start one below the estimate
-    int s_first = (int)fmin((double)nh, floor(vk * (double)p.nt * p.dt * 0.15915494309189535)) - 1;
+    const double vkx2 = ps_vkx2(p.vel, ps_kx(k, p.T, p.dx));  // (vmig*kx/2)^2   (:411)
+    const double vk = sqrt(vkx2);
+    // pairs below s ~ vk nt dt / 2 pi are evanescent for every tau (:412); start two below the estimate (ties are
+    // decided by the exact comparison below, never by this estimate)
+    int s_first = (int)fmin((double)nh, floor(vk * (double)p.nt * p.dt * 0.15915494309189535)) - 2;
     if (s_first < 0) s_first = 0;
 
     int pass = 0;
@@ -359,8 +377,9 @@ __global__ void __launch_bounds__(PP_THREADS, 2) phsh_const_pair_kernel(const __
             float2 z64 = z[i];
             if (s < nh) {
                 const double w = ps_omega(s, p.nt, p.dt);
-                if (vkx2 < w * w) {  // propagating (:412)
-                    const double phi = w * p.dt * sqrt(1.0 - vkx2 / (w * w));  // = -phase (:415); cp = e^{+i phi}
+                const double w2 = __dmul_rn(w, w);
+                if (vkx2 < w2) {  // propagating (:412)
+                    const double phi = ps_phi(w, p.dt, vkx2, w2);  // = -phase (:415); cp = e^{+i phi}
                     double sn, cs;
                     sincos(phi, &sn, &cs);
                     z[i] = make_float2((float)cs, (float)sn);

@@ -445,7 +445,10 @@ def denoise(self, vert_win=1, hor_win=10, noise=None, ftype='wiener'):
             if (flag & 1) and total != 0.0:                           # noise / 0 with noise != 0: numpy's 'divide' error
                 raise ValueError('Could not compute variance, specify noise for denoise')
         if was_device:
-            self.data = out if x.dtype == torch.float64 else out.float()
+            # scipy's wiener returns float64; inside process()'s chain (_b200_reference_dtypes) the float64 result is
+            # kept like restack / nmo do, a bare float32 device tensor keeps its dtype
+            keep64 = x.dtype == torch.float64 or getattr(self, '_b200_reference_dtypes', False)
+            self.data = out if keep64 else out.float()
         else:
             self.data = device.to_host(out, np.float64)
     elif ftype == 'median':

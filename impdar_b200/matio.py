@@ -6,8 +6,11 @@ its dtype-preservation rules; ``RadarFlags.to_matlab / from_matlab`` follow Rada
 The container itself is scipy.io's MATLAB v5 reader / writer, exactly what the reference uses.  What changes for the
 device path: the radargram of a loaded file lands in page-locked memory (when a CUDA device is present), so the upload
 that follows is one DMA at PCIe speed instead of a staged copy.  Picks are interpretation state outside the hot path:
-a ``picks`` struct found in a file is exposed raw as ``dat.picks_struct`` and is NOT written back by ``save`` (an
-object with a real ``picks.to_struct()`` - ImpDAR's own RadarData - is written like the reference does).
+a ``picks`` struct found in a file is kept raw as ``dat.picks_struct`` and ``save`` writes it back verbatim as long as
+the radargram still has the axes it was loaded with (load -> filter / migrate -> save keeps the picks); once a step has
+changed the trace or sample axis the raw struct is stale, and ``save`` warns (RuntimeWarning) instead of silently
+dropping or corrupting it.  An object with a real ``picks.to_struct()`` - ImpDAR's own RadarData - is written like the
+reference does.
 """
 import numpy as np
 
@@ -122,7 +125,8 @@ def load_mat(fn_mat, pinned=True):
     dat.flags = RadarFlags()
     dat.flags.from_matlab(mat['flags'])
     dat.picks = None
-    dat.picks_struct = mat['picks'] if 'picks' in mat else None      # raw, for inspection only (see module docstring)
+    dat.picks_struct = mat['picks'] if 'picks' in mat else None      # raw MATLAB struct; save() writes it back verbatim
+    dat._picks_axes = (int(dat.data.shape[0]), int(dat.data.shape[1]))  # ... while the radargram keeps these axes
     check_attrs(dat)
     return dat
 
@@ -144,8 +148,31 @@ def save(self, fn):
     if device.is_device_array(mat['data']):                           # device-resident lane: download for the file
         mat['data'] = mat['data'].cpu().numpy()
     picks = getattr(self, 'picks', None)
+    picks_struct = getattr(self, 'picks_struct', None)
     if picks is not None:
         mat['picks'] = picks.to_struct()
+    elif picks_struct is not None:
+        # load_mat keeps the file's picks as the raw MATLAB struct (no Picks object on this side of the seam): it goes
+        # back into the file verbatim, so load_mat -> process -> save does not lose picks, as long as the per-trace
+        # arrays still match the radargram; after a step that changed the trace or sample axis they are stale, and
+        # dropping them silently would lose data without a trace - warn loudly instead.
+        ok = True
+        try:
+            samp = picks_struct['samp1'][0, 0]
+            tnum = int(np.shape(mat['data'])[1])
+            ok = samp.size == 0 or samp.ndim < 2 or samp.shape[1] == tnum
+            loaded = getattr(self, '_picks_axes', None)
+            if loaded is not None and loaded != (int(np.shape(mat['data'])[0]), tnum):
+                ok = False
+        except Exception:
+            ok = False
+        if ok:
+            mat['picks'] = picks_struct
+        else:
+            import warnings
+            warnings.warn('%s: the picks loaded with this file no longer match the radargram (the trace or sample axis '
+                          'changed) and impdar_b200 carries no Picks object to update them; they are NOT written' % fn,
+                          RuntimeWarning, stacklevel=2)
     flags = self.flags if self.flags is not None else RadarFlags()
     mat['flags'] = flags.to_matlab()
 

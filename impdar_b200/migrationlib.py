@@ -65,12 +65,19 @@ def _mean_trace_spacing(dat):
     return float(np.mean(trace_int))
 
 
-def _finish(dat, out_dev, np_dtype, was_device):
+def _finish(dat, out_dev, np_dtype, was_device, in_torch_dtype=None):
+    """Hand the result back the way the input came: a host array of the reference's dtype, or - device-resident lane -
+    a CUDA tensor of the INPUT tensor's dtype (a float64 tensor stays float64; the migrations compute in float32, so its
+    values are float32-accurate - the documented dtype policy - but the dtype never narrows silently)."""
     if was_device:
-        dat.data = out_dev
+        dat.data = out_dev if in_torch_dtype is None or out_dev.dtype == in_torch_dtype else out_dev.to(in_torch_dtype)
     else:
         dat.data = device.to_host(out_dev, np_dtype)
     return dat
+
+
+def _torch_dtype(data):
+    return data.dtype if device.is_device_array(data) else None
 
 
 # ---------------------------------------------------------------------------------------- Kirchhoff
@@ -193,7 +200,9 @@ def migrationKirchhoff(dat, vel=1.69e8, nearfield=False):
     _check_data_shape(dat)
     start = time.time()
     if device.is_device_array(dat.data):
-        dat.data = kirchhoff_device(device.to_device(dat.data), dat.travel_time, dat.dist, vel, nearfield)
+        in_dt = dat.data.dtype
+        out = kirchhoff_device(device.to_device(dat.data), dat.travel_time, dat.dist, vel, nearfield)
+        dat.data = out if out.dtype == in_dt or not in_dt.is_floating_point else out.to(in_dt)
     else:
         dat.data = kirchhoff_host(dat.data, dat.travel_time, dat.dist, vel, nearfield)
     print('Kirchhoff Migration of %.0fx%.0f matrix complete in %.2f seconds'
@@ -289,9 +298,10 @@ def migrationStolt(dat, vel=1.68e8, htaper=100, vtaper=1000):
     in_dtype = _np_dtype(dat.data)
     trunc_int = in_dtype is not None and np.issubdtype(in_dtype, np.integer)  # .astype(dat.data.dtype), :157
     out_dtype = np.float32 if in_dtype == np.float32 else np.float64         # dtype of np.fft.irfft2
+    in_tdt = _torch_dtype(dat.data)
     x = device.to_device(dat.data)
     out = stolt_device(x, dat.dt, _mean_trace_spacing(dat), vel, htaper, vtaper, trunc_int)
-    _finish(dat, out, out_dtype, was_device)
+    _finish(dat, out, out_dtype, was_device, in_tdt)
     print('Stolt Migration of %.0fx%.0f matrix complete in %.2f seconds'
           % (dat.snum, dat.tnum, time.time() - start))
     return dat
@@ -414,6 +424,7 @@ def migrationPhaseShift(dat, vel=1.69e8, vel_fn=None, htaper=100, vtaper=1000, *
     _check_data_shape(dat)
     start = time.time()
     was_device = device.is_device_array(dat.data)
+    in_tdt = _torch_dtype(dat.data)
     _reject_integer_inplace(dat)
     dx = _mean_trace_spacing(dat)
     if vel_fn is not None:
@@ -437,7 +448,7 @@ def migrationPhaseShift(dat, vel=1.69e8, vel_fn=None, htaper=100, vtaper=1000, *
     else:
         x = device.to_device(dat.data)
         out = phase_shift_device(x, dat.dt, dx, dat.travel_time, vmig, htaper, vtaper)
-    _finish(dat, out, np.float64, was_device)
+    _finish(dat, out, np.float64, was_device, in_tdt)
     print('Phase-Shift Migration of %.0fx%.0f matrix complete in %.2f seconds'
           % (dat.snum, dat.tnum, time.time() - start))
     return dat
@@ -453,11 +464,17 @@ def migrationTimeWavenumber(dat, vel=1.69e8, vel_fn=None, htaper=100, vtaper=100
     was_device = device.is_device_array(dat.data)
     in_dtype = _reject_integer_inplace(dat)
     lib = _lib.load()
-    x = device.to_device(dat.data)
+    # a pure elementwise product: float64 radargrams (host or device) are tapered in float64, exactly like numpy
+    f64 = (in_dtype == np.float64) if in_dtype is not None else (dat.data.dtype == torch.float64)
+    x = device.to_device(dat.data, torch.float64 if f64 else torch.float32)
     S, T = x.shape
     out = x if was_device else torch.empty_like(x)
-    rc = lib.impdar_taper_f32(device.ptr(x), device.ptr(out), S, T, 1, float(htaper), float(vtaper), 0,
-                              device.current_stream_ptr())
+    if f64:
+        rc = lib.impdar_taper_f64(device.ptr(x), device.ptr(out), S, T, 1, float(htaper), float(vtaper),
+                                  device.current_stream_ptr())
+    else:
+        rc = lib.impdar_taper_f32(device.ptr(x), device.ptr(out), S, T, 1, float(htaper), float(vtaper), 0,
+                                  device.current_stream_ptr())
     _lib.check(rc)
     _finish(dat, out, in_dtype, was_device)
     print('Time-Wavenumber Migration of %.0fx%.0f matrix complete in %.2f seconds'

@@ -99,37 +99,55 @@ def run_device_chain(dats, steps, n_streams=3):
         dat.data = out if out.dtype == np_dtype else out.astype(np_dtype)
         pending[slot] = None
 
-    for i, dat in enumerate(dats):
-        slot = i % n_streams
-        finish(slot)
-        if device.is_device_array(dat.data):
-            _run_chain_on_device(dat, steps)      # already device resident: stays there, caller's stream
-            continue
-        src = np.asarray(dat.data)
-        if not np.issubdtype(src.dtype, np.floating):
-            # integer radargrams need the reference's cast-back (truncation) after every step: per-step path
-            _run_chain_on_device(dat, steps)
-            continue
-        final_dtype = _host_dtype_after(steps, src.dtype, dat)
-        with torch.cuda.stream(streams[slot]):
-            dat.data = device.to_device(src, torch.float32 if src.dtype == np.float32 else torch.float64)
-            dat._b200_reference_dtypes = True       # restack / nmo produce the reference's float64 on the device
-            try:
+    # Exception safety (the reference processes profile after profile: when a step raises for profile i, profiles
+    # < i are completely processed and profile i keeps whatever state the failing step left): every profile already
+    # queued is finished on the way out, and the failing profile gets a host array back - the partial result the
+    # device holds (downloaded, like the reference's partially processed dat.data), or its untouched input.
+    try:
+        for i, dat in enumerate(dats):
+            slot = i % n_streams
+            finish(slot)
+            if device.is_device_array(dat.data):
+                _run_chain_on_device(dat, steps)      # already device resident: stays there, caller's stream
+                continue
+            src = np.asarray(dat.data)
+            if not np.issubdtype(src.dtype, np.floating):
+                # integer radargrams need the reference's cast-back (truncation) after every step: per-step path
                 _run_chain_on_device(dat, steps)
-            finally:
-                del dat._b200_reference_dtypes
-            res = dat.data
-            want = torch.float64 if final_dtype == np.float64 else torch.float32
-            if res.dtype != want:
-                res = res.to(want)                 # cast on the device: the download is one DMA into pinned memory
-            host = torch.empty(res.shape, dtype=res.dtype, pin_memory=True)
-            host.copy_(res.contiguous(), non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(streams[slot])
-        dat.data = None                             # filled in by finish(); never left pointing at stale input
-        pending[slot] = (dat, host, ev, final_dtype)
-    for slot in range(n_streams):
-        finish(slot)
+                continue
+            final_dtype = _host_dtype_after(steps, src.dtype, dat)
+            with torch.cuda.stream(streams[slot]):
+                try:
+                    dat.data = device.to_device(src, torch.float32 if src.dtype == np.float32 else torch.float64)
+                    dat._b200_reference_dtypes = True   # restack / nmo produce the reference's float64 on the device
+                    try:
+                        _run_chain_on_device(dat, steps)
+                    finally:
+                        del dat._b200_reference_dtypes
+                    res = dat.data
+                    want = torch.float64 if final_dtype == np.float64 else torch.float32
+                    if res.dtype != want:
+                        res = res.to(want)             # cast on the device: the download is one DMA into pinned memory
+                    host = torch.empty(res.shape, dtype=res.dtype, pin_memory=True)
+                    host.copy_(res.contiguous(), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(streams[slot])
+                except BaseException:
+                    partial = dat.data
+                    if device.is_device_array(partial):
+                        try:
+                            streams[slot].synchronize()
+                            dat.data = partial.cpu().numpy()
+                        except Exception:
+                            dat.data = src
+                    elif partial is None:
+                        dat.data = src
+                    raise
+            dat.data = None                             # filled in by finish(); never left pointing at stale input
+            pending[slot] = (dat, host, ev, final_dtype)
+    finally:
+        for slot in range(n_streams):
+            finish(slot)
 
 
 def process(RadarDataList, interp=None, rev=False, vbp=None, hfilt=None, ahfilt=None, nmo=None, crop=None,

@@ -57,6 +57,10 @@ int impdar_b200_kernel_timer_read(const char *kernel, double *total_ms, int *lau
  * reference's cast back to an integer input dtype (truncation toward zero).  x == y allowed.          */
 int impdar_taper_f32(const float *x, float *y, int snum, int tnum, int batch, double htaper,
                      double vtaper, int trunc_int, void *stream);
+/* float64 radargrams: y = x * (h[t] * v[s]), one rounding per product in the reference's order (the time-wavenumber
+ * stub's in-place `data *= H * V`, mig_python.py:330-335) - bit-exact against numpy.                   */
+int impdar_taper_f64(const double *x, double *y, int snum, int tnum, int batch, double htaper, double vtaper,
+                     void *stream);
 
 /* ----------------------------------------------- horizontalfilt (_RadarDataFiltering.py:93-135) --- */
 /* y[s,t] = x[s,t] - (T)(mean(x[s, htr1:htrn]) * taper[s]);  taper: device, snum doubles.
@@ -71,8 +75,9 @@ int impdar_hfilt_f64(const double *x, double *y, int snum, int tnum, int batch, 
  * filtfilt([.25]*4, 1, .) amounts to on the odd-extended mean trace, the exp taper, the subtraction.
  * Requires snum > 12 (scipy's padlen).  workspace: impdar_ahfilt_workspace_bytes() bytes (may be 0). */
 size_t impdar_ahfilt_workspace_bytes(int snum, int tnum, int batch);
-/* Testing hook: 0 = auto (prefix-sum strip kernel; warp-sliding kernel for windows wider than its buffer), 1 = the
- * one-row-per-CTA kernel, 3 = the warp-sliding kernel.                                                              */
+/* Testing hook: 0 = auto (register-scan strip kernel for float radargrams with tnum % 4 == 0, first strip kernel
+ * otherwise; warp-sliding kernel for windows wider than their buffers), 1 = the one-row-per-CTA kernel, 2 = the first
+ * strip kernel, 3 = the warp-sliding kernel.                                                                        */
 int impdar_ahfilt_force_rowwise(int on);
 int impdar_ahfilt_f32(const float *x, float *y, int snum, int tnum, int batch, int window_size,
                       const double *taper, void *workspace, size_t workspace_bytes, void *stream);

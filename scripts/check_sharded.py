@@ -1,44 +1,68 @@
-"""torchrun check of the multi-GPU Kirchhoff: the pipelined exchange (bottom-up row chunks: broadcast | kernels |
-all-gather overlapped) must return bit for bit what the three phases back to back return; prints both timings.
+"""torchrun check of the multi-GPU Kirchhoff on real GPUs: the sharded result (halo exchange: every rank receives only
+its window of input columns; output blocks gathered to rank 0; exchanges overlapped with the kernels in bottom-up row
+chunks) must equal, BIT FOR BIT, the unsharded image that rank 0 computes alone, for every pipeline depth, and so must
+the round-1 scheme (full broadcast + all-gather).  Prints the timings of both schemes.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/check_sharded.py [S T]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
-from impdar_b200 import parallel, synthetic
+from impdar_b200 import parallel, synthetic, migrationlib as ml
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
-dist.init_process_group("nccl")
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank))))
 S, T = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (4096, 16384)
 tt, dk, _ = synthetic.geometry(S, T)
-full = synthetic.diffractor_radargram(S, T, seed=9, n_diffractors=64)
+VEL = 1.69e8
+if rank == 0:
+    full = synthetic.diffractor_radargram(S, T, seed=9, n_diffractors=64)
+    whole = ml.kirchhoff_device(full, tt, dk, VEL, False)          # the unsharded image
+    kern = ml.kirchhoff_last_kernel()
+else:
+    full = whole = None
 
-def run(chunks):
-    x = full.clone() if rank == 0 else torch.zeros((S, T), dtype=torch.float32, device="cuda")
-    return parallel.kirchhoff_sharded_device(x, tt, dk, 1.69e8, False, rank=rank, world=world, pipeline_chunks=chunks), x
+def x_for(exchange):
+    if rank == 0:
+        return full.clone()
+    if exchange == "broadcast":
+        return torch.zeros((S, T), dtype=torch.float32, device="cuda")
+    return torch.empty((1, 1), dtype=torch.float32, device="cuda").expand(S, T)
 
-def timed(chunks, n=3):
-    run(chunks); torch.cuda.synchronize(); dist.barrier()
+def run(exchange, chunks):
+    x = x_for(exchange)
+    out = parallel.kirchhoff_sharded_device(x, tt, dk, VEL, False, rank=rank, world=world, pipeline_chunks=chunks,
+                                            exchange=exchange, gather=True if exchange == "broadcast" else 'src')
+    torch.cuda.synchronize()
+    return out
+
+def timed(exchange, chunks, n=3):
+    run(exchange, chunks); dist.barrier()
     ts = []
     for _ in range(n):
-        x = full.clone() if rank == 0 else torch.zeros((S, T), dtype=torch.float32, device="cuda")
+        x = x_for(exchange)
         torch.cuda.synchronize(); dist.barrier()
         a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
         a.record()
-        parallel.kirchhoff_sharded_device(x, tt, dk, 1.69e8, False, rank=rank, world=world, pipeline_chunks=chunks)
+        parallel.kirchhoff_sharded_device(x, tt, dk, VEL, False, rank=rank, world=world, pipeline_chunks=chunks,
+                                          exchange=exchange, gather=True if exchange == "broadcast" else 'src')
         b.record(); torch.cuda.synchronize()
         t = torch.tensor([a.elapsed_time(b)], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ts.append(t.item())
     return min(ts)
 
-ref, _ = run(1)
-for chunks in (4, 8, 16):
-    got, x = run(chunks)
-    same = bool(torch.equal(got, ref)) and bool(torch.equal(x, full))
-    t = torch.tensor([0.0 if same else 1.0], device="cuda"); dist.all_reduce(t)
-    if rank == 0:
-        print("pipeline_chunks=%d identical on all ranks: %s" % (chunks, t.item() == 0.0), flush=True)
-for chunks in (1, 4, 8, 16):
-    ms = timed(chunks)
-    if rank == 0:
-        print("%d x %d on %d GPUs, pipeline_chunks=%d: %.2f ms" % (S, T, world, chunks, ms), flush=True)
+if rank == 0:
+    print("%d x %d on %d GPUs; single-GPU kernel: %s" % (S, T, world, kern), flush=True)
+for exchange in ("halo", "broadcast"):
+    for chunks in (1, 4, 8):
+        got = run(exchange, chunks)
+        ok = torch.tensor([1.0 if (rank != 0 or torch.equal(got, whole)) else 0.0], device="cuda")
+        if exchange == "broadcast" and rank != 0:       # every rank holds the image in the round-1 scheme
+            ok[0] = 1.0 if got.shape == (S, T) else 0.0
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("exchange=%s pipeline_chunks=%d: sharded == unsharded bit for bit: %s" % (exchange, chunks, ok.item() == 1.0), flush=True)
+for exchange in ("halo", "broadcast"):
+    for chunks in (1, 4, 8):
+        ms = timed(exchange, chunks)
+        if rank == 0:
+            print("exchange=%s pipeline_chunks=%d: %.2f ms" % (exchange, chunks, ms), flush=True)
 dist.destroy_process_group()

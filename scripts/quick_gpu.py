@@ -47,6 +47,19 @@ if 'filters' in which:
     x1=x[0].contiguous()
     ms=ev(lambda: fl.filtfilt_device(x1,'f32',b,a)); print(f'filtfilt B=1: {ms:.3f} ms {S*T*8/ms*1e3/1e9:.1f} GB/s',flush=True)
     del x
+if 'ahfilt' in which:
+    from impdar_b200 import _lib
+    lib=_lib.load()
+    for (S,T,B) in [(2048,8192,8),(2048,8192,1)]:
+        x=torch.randn(B,S,T,device='cuda') if B>1 else torch.randn(S,T,device='cuda')
+        tp=np.exp(-np.arange(S)*0.01*0.05)
+        for w in (1000,100):
+            for mode,name in ((0,'fast'),(2,'strip')):
+                lib.impdar_ahfilt_force_rowwise(mode)
+                ms=ev(lambda: fl.adaptivehfilt_device(x,'f32',tp,w),n=5,warm=2)
+                lib.impdar_ahfilt_force_rowwise(0)
+                print(f'ahfilt {B}x{S}x{T} w={w} {name}: {ms:.3f} ms {B*S*T*8/ms*1e3/1e9:.1f} GB/s ({B*S*T*8/ms*1e3/1e9/6552:.1%} of HBM peak)',flush=True)
+        del x
 if 'phsh' in which:
     for (S,T) in [(1024,2048),(4096,16384)]:
         x=torch.randn(S,T,device='cuda'); tt,dist=geom(S,T)

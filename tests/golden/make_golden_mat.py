@@ -3,6 +3,8 @@
   mat_ref_saved.mat    small_data.mat loaded, cropped, nmo'ed and flagged by the reference, saved by RadarData.save
   mat_ref_resaved.mat  that file loaded and saved once more by the reference (what a load -> save round trip must give)
   mat_ref_f32.mat      a float32 radargram whose data_dtype is float32 (dtype preservation)
+  mat_ref_picks.mat    small_data_picks.mat (a picked profile) loaded and saved by the reference: Picks.to_struct()
+  mat_ref_picks_resaved.mat  that file through the reference's load -> save once more
       python tests/golden/make_golden_mat.py"""
 import contextlib
 import io
@@ -38,4 +40,7 @@ d.data = d.data.astype(np.float32)
 d.data_dtype = np.dtype(np.float32)
 d.elev = None
 d.save(os.path.join(HERE, 'mat_ref_f32.mat'))
+SRC_P = os.path.join(os.path.dirname(SRC), "small_data_picks.mat")
+RadarData(SRC_P).save(os.path.join(HERE, 'mat_ref_picks.mat'))
+RadarData(os.path.join(HERE, 'mat_ref_picks.mat')).save(os.path.join(HERE, 'mat_ref_picks_resaved.mat'))
 print('wrote', [f for f in os.listdir(HERE) if f.startswith('mat_')])

@@ -180,7 +180,7 @@ def test_ahfilt_strip_vs_oracle(S, T, w):
     got = fl.adaptivehfilt_device(xd, 'f32', tp, w).cpu().numpy()
     lib = _lib.load()
     others = []
-    for mode in (1, 3):                     # 1 = one-row-per-CTA kernel, 3 = warp-sliding kernel
+    for mode in (1, 2, 3):                  # 1 = one-row-per-CTA kernel, 2 = first strip kernel, 3 = warp-sliding kernel
         lib.impdar_ahfilt_force_rowwise(mode)
         try:
             others.append(fl.adaptivehfilt_device(xd, 'f32', tp, w).cpu().numpy())
@@ -399,3 +399,28 @@ def test_denoise_median_large_vs_oracle():
     assert np.array_equal(d.data, want)
     with pytest.raises(ValueError):
         d.denoise(vert_win=17, hor_win=16, ftype='median')  # 272 samples > the 256 the kernel holds
+
+
+def test_tk_float64_is_exact_and_device_dtypes_never_narrow():
+    """The time-wavenumber stub is `data *= H * V` (mig_python.py:330-335): a float64 radargram is tapered in float64,
+    bit for bit numpy's result, on the host lane and on the device lane; a float64 CUDA tensor comes back float64 from
+    every migration (values float32-accurate where the path computes in float32 - the documented dtype policy)."""
+    import torch
+    from oracle import migration as om
+    d = synthetic_dat(70, 90, seed=4, dtype=np.float64)
+    want = om.time_wavenumber(d.data, 13, 9)
+    d.migrate(mtype='tk', htaper=13, vtaper=9)
+    assert d.data.dtype == np.float64 and np.array_equal(d.data, want)
+    d = synthetic_dat(70, 90, seed=4, dtype=np.float64)
+    d.data = torch.from_numpy(d.data).cuda()
+    d.migrate(mtype='tk', htaper=13, vtaper=9)
+    assert d.data.dtype == torch.float64 and np.array_equal(d.data.cpu().numpy(), want)
+    for mtype in ('stolt', 'kirch', 'phsh'):
+        d = synthetic_dat(64, 96, seed=5, dtype=np.float64)
+        d.data = torch.from_numpy(d.data).cuda()
+        d.migrate(mtype=mtype)
+        assert d.data.is_cuda and d.data.dtype == torch.float64, mtype
+        d = synthetic_dat(64, 96, seed=5, dtype=np.float32)
+        d.data = torch.from_numpy(d.data).cuda()
+        d.migrate(mtype=mtype)
+        assert d.data.is_cuda and d.data.dtype == torch.float32, mtype

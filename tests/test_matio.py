@@ -157,3 +157,42 @@ def test_loaded_radargram_is_page_locked_and_feeds_the_device_chain():
     d.trig = np.zeros(d.tnum)
     d.hfilt(ftype='hfilt', bounds=(0, d.tnum))
     assert d.data.dtype == np.float32 and d.flags.hfilt[0] == 1
+
+
+def _struct_equal(x, y):
+    assert x.dtype.names == y.dtype.names and x.shape == y.shape
+    for f in x.dtype.names:
+        a, b = x[f][0][0], y[f][0][0]
+        if a.dtype.names:                      # nested struct (pickparams)
+            _struct_equal(a, b)
+        elif a.dtype == object:
+            assert str(a) == str(b), f
+        else:
+            assert a.shape == b.shape and np.array_equal(a, b, equal_nan=a.dtype.kind == 'f'), f
+
+
+def test_picks_survive_load_filter_save(tmp_path):
+    """A picked profile written by the reference: load_mat -> (a step that keeps both axes) -> save writes the picks back
+    verbatim, equal to what the reference's own load -> save round trip writes; once a step has changed an axis the
+    stale struct is not written and save says so."""
+    import warnings
+    src = os.path.join(GOLDEN_DIR, 'mat_ref_picks.mat')
+    d = impdar_b200.load_mat(src, pinned=False)
+    assert d.picks is None and d.picks_struct is not None
+    d.flags.bpass = np.array([1., 2., 10.])              # host-side stand-in for an in-place filter step
+    out = os.path.join(str(tmp_path), 'picks_again.mat')
+    with warnings.catch_warnings():
+        warnings.simplefilter('error')
+        d.save(out)
+    got = loadmat(out)
+    want = loadmat(os.path.join(GOLDEN_DIR, 'mat_ref_picks_resaved.mat'))
+    assert 'picks' in got
+    _struct_equal(got['picks'], want['picks'])
+    _struct_equal(got['picks'], loadmat(src)['picks'])
+    # an axis changed (hcrop-like): the raw struct no longer describes the radargram
+    d2 = impdar_b200.load_mat(src, pinned=False)
+    d2.data = np.ascontiguousarray(d2.data[:, :30])
+    d2.tnum = 30
+    with pytest.warns(RuntimeWarning, match='picks'):
+        d2.save(os.path.join(str(tmp_path), 'picks_cropped.mat'))
+    assert 'picks' not in loadmat(os.path.join(str(tmp_path), 'picks_cropped.mat'))

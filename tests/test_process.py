@@ -134,3 +134,27 @@ def test_process_device_resident_input_stays_on_device():
     r.vertical_band_pass(2, 10)
     r.migrate(mtype='stolt')
     assert np.array_equal(d.data.cpu().numpy(), r.data)
+
+
+@pytest.mark.gpu
+def test_process_failing_profile_leaves_the_others_processed():
+    """One profile in a longer list than n_streams makes a step raise (denoise on constant data: zero local variance).
+    Like the reference's serial loop, every earlier profile is completely processed and holds a host array; nothing is
+    left with data = None, and the failing profile keeps a host array (the state before the failing step)."""
+    dats = [synthetic_dat(64, 96, seed=20 + i) for i in range(6)]
+    ref = [synthetic_dat(64, 96, seed=20 + i) for i in range(6)]
+    bad = 4
+    dats[bad].data[:] = 1.0
+    dats[bad].data[:, 40:] = np.arange(64, dtype=np.float32)[:, None]    # zero local variance on the left, not overall
+    with pytest.raises(ValueError):
+        impdar_b200.process.process(dats, rev=True, denoise=(1, 3), n_streams=3)
+    for i, (d, r) in enumerate(zip(dats, ref)):
+        assert isinstance(d.data, np.ndarray), "profile %d was left without a host array" % i
+        if i < bad:
+            r.reverse()
+            r.denoise(1, 3)
+            # the Wiener noise estimate is reduced with float64 atomics: equal to rounding, not bit for bit
+            assert d.data.dtype == r.data.dtype and np.allclose(d.data, r.data, rtol=1e-12, atol=0)
+        elif i > bad:
+            assert np.array_equal(d.data, r.data)        # never started
+    assert dats[bad].data.shape == (64, 96) and np.all(np.isfinite(dats[bad].data))
