@@ -467,15 +467,25 @@ __global__ void __launch_bounds__(256, 2) ahfilt_fast_kernel(const float *__rest
     if (tid == 0) Q[0] = 0.0;
     for (int r = r0; r <= r1; ++r) {
         // ---- thread-local inclusive scan of 16 contiguous elements, in float64 registers
+        // (four independent chains of four, then the chain offsets: depth 6 instead of 16 dependent float64 adds)
         double v[AHF_E];
-        double run = 0.0;
 #pragma unroll
         for (int v4 = 0; v4 < AHF_E / 4; ++v4) {
-            run += (double)nxt[v4].x; v[4 * v4 + 0] = run;
-            run += (double)nxt[v4].y; v[4 * v4 + 1] = run;
-            run += (double)nxt[v4].z; v[4 * v4 + 2] = run;
-            run += (double)nxt[v4].w; v[4 * v4 + 3] = run;
+            v[4 * v4 + 0] = (double)nxt[v4].x;
+            v[4 * v4 + 1] = v[4 * v4 + 0] + (double)nxt[v4].y;
+            v[4 * v4 + 2] = v[4 * v4 + 1] + (double)nxt[v4].z;
+            v[4 * v4 + 3] = v[4 * v4 + 2] + (double)nxt[v4].w;
         }
+        {
+            const double o1 = v[3], o2 = o1 + v[7], o3 = o2 + v[11];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                v[4 + e] += o1;
+                v[8 + e] += o2;
+                v[12 + e] += o3;
+            }
+        }
+        const double run = v[AHF_E - 1];
         if (r < r1) load_segment(r + 1);
         float2 xc[AHF_PAIRS];
         {
@@ -494,7 +504,17 @@ __global__ void __launch_bounds__(256, 2) ahfilt_fast_kernel(const float *__rest
         if (lane == 31) wtot[warp] = inc;
         __syncthreads();                     // also: the previous row's window reads of Q and ring reads are done
         double off = inc - run;
-        for (int u = 0; u < warp; ++u) off += wtot[u];
+        {
+            // exclusive scan of the eight warp totals: every warp does it redundantly in its first eight lanes
+            double wv = (lane < 8) ? wtot[lane] : 0.0;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, wv, o);
+                if (lane >= o) wv += up;
+            }
+            const double wprev = __shfl_sync(0xffffffffu, wv, max(warp - 1, 0));
+            if (warp > 0) off += wprev;
+        }
         {
             double *qc = Q + 17 * tid + 1;   // ahf_pad(16 tid + 1 + e) = 17 tid + 1 + e for e < 15, + 1 more for e = 15
 #pragma unroll

@@ -35,6 +35,11 @@ extern "C" int impdar_taper_f32(const float *x, float *y, int S, int T, int batc
 
 namespace impdar {
 
+// phaseshift_tc.cu: constant velocity as a per-kx complex matrix product on the tensor cores
+size_t phsh_tc_workspace_bytes(int nt, int K);
+int phsh_const_tc_launch(const float2 *FK, float2 *TK, int nt, int K, int S, int T, double dt, double dx, double vel,
+                         float inv_s, void *ws, cudaStream_t st);
+
 #define IMPDAR_CUFFT(call)                                                                  \
     do {                                                                                    \
         cufftResult r__ = (call);                                                           \
@@ -517,7 +522,7 @@ __global__ void __launch_bounds__(128) phsh_layered_nyq_kernel(const __grid_cons
     }
 }
 
-static int g_phsh_legacy = 0;  // testing hook: 1 = the one-bin-per-state kernels
+static int g_phsh_legacy = 0;  // testing hook: 0 auto (tensor-core constant velocity), 1 = the one-bin-per-state kernels, 3 = pair kernels only
 
 struct PhshPlans {
     cufftHandle r2c = 0, c2c = 0, c2r = 0;
@@ -572,7 +577,7 @@ size_t impdar_phsh_workspace_bytes(int S, int T) {
     const size_t fk = nt * K * sizeof(float2);
     const size_t tk = (size_t)S * K * sizeof(float2);
     const size_t real = (size_t)S * (size_t)T * sizeof(float);
-    return fk + (tk > real ? tk : real) + 2048;
+    return fk + (tk > real ? tk : real) + phsh_tc_workspace_bytes((int)nt, (int)K) + 4096;
 }
 
 int impdar_phsh_f32(const float *data, float *out, int S, int T, double dt, double dx, double vel,
@@ -612,7 +617,17 @@ int impdar_phsh_f32(const float *data, float *out, int S, int T, double dt, doub
     p.FK = FK; p.TK = TK; p.nt = nt; p.K = K; p.S = S; p.T = T;
     p.dt = dt; p.dx = fabs(dx); p.vel = vel; p.vmig = vmig; p.thr2 = thr2;
     p.inv_s = (float)(1.0 / ((double)S * (double)T));  // /snum (:490-492) and numpy ifft's 1/tnum (:282)
-    if (!g_phsh_legacy) {
+    if ((g_phsh_legacy == 0 || g_phsh_legacy == 2) && vmig == nullptr && nt >= 64) {
+        // constant velocity on the tensor cores (phaseshift_tc.cu)
+        const size_t tk_bytes = (size_t)S * K * sizeof(float2), real_bytes = (size_t)S * T * sizeof(float);
+        char *w3 = w2 + (((tk_bytes > real_bytes ? tk_bytes : real_bytes) + 255) & ~(size_t)255);
+        rc = phsh_const_tc_launch(FK, TK, nt, K, S, T, dt, fabs(dx), vel, p.inv_s, w3, st);
+        if (rc) return rc;
+        IMPDAR_CUFFT(cufftExecC2R(pl.c2r, (cufftComplex *)TK, out));  // kx -> x
+        count_launch(1);
+        return IMPDAR_B200_OK;
+    }
+    if (g_phsh_legacy != 1) {
         if (vmig == nullptr) {
             ktimer_begin("phsh_const_pair_kernel", st);
             phsh_const_pair_kernel<<<K, PP_THREADS, 0, st>>>(p);
@@ -647,8 +662,11 @@ int impdar_phsh_f32(const float *data, float *out, int S, int T, double dt, doub
     return IMPDAR_B200_OK;
 }
 
-int impdar_phsh_set_legacy(int on) {
-    g_phsh_legacy = on ? 1 : 0;
+int impdar_phsh_set_legacy(int mode) {
+    IMPDAR_CHECK_ARG(mode >= 0 && mode <= 3, "phsh_set_legacy: 0 automatic (constant velocity on the tensor cores - tcgen05, "
+                                             "3xTF32 - layered velocity on the (+w, -w) pair kernel), 1 first-generation "
+                                             "kernels, 2 = 0, 3 pair kernels for both");
+    g_phsh_legacy = mode;
     return IMPDAR_B200_OK;
 }
 

@@ -158,7 +158,19 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
     dev, dt = x.device, x.dtype
     empty = torch.empty(0, dtype=dt, device=dev)
     is_src = rank == src
-    # ---- 1. input windows, every chunk enqueued up front (the collective stream runs them back to back)
+    # ---- 1. input windows, every chunk enqueued up front (the collective stream runs them back to back).  On `src` the
+    # packing of the other ranks' column slabs and, later, the filing of their finished rows run on a side stream: the
+    # compute stream of `src` only ever waits for the kernels of its own range.
+    use_side = x.is_cuda
+    if use_side:
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(main)
+
+    def on_side():
+        import contextlib
+        return torch.cuda.stream(side) if use_side else contextlib.nullcontext()
+
     win = x[:, c0:c1] if is_src else torch.empty((S, c1 - c0), dtype=dt, device=dev)
     arrive = {}
     u_hi = S
@@ -170,13 +182,16 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
         rows = u_hi - u0
         if is_src:
             sizes = [0 if r == src else rows * (windows[r][1] - windows[r][0]) for r in range(world)]
-            send = torch.empty(sum(sizes), dtype=dt, device=dev)
-            off = 0
-            for r in range(world):
-                if sizes[r]:
-                    send[off:off + sizes[r]].view(rows, -1).copy_(x[u0:u_hi, windows[r][0]:windows[r][1]])
-                    off += sizes[r]
-            arrive[j] = dist.all_to_all_single(empty, send, [0] * world, sizes, group=group, async_op=True)
+            with on_side():
+                send = torch.empty(sum(sizes), dtype=dt, device=dev)
+                off = 0
+                for r in range(world):
+                    if sizes[r]:
+                        send[off:off + sizes[r]].view(rows, -1).copy_(x[u0:u_hi, windows[r][0]:windows[r][1]])
+                        off += sizes[r]
+                arrive[j] = dist.all_to_all_single(empty, send, [0] * world, sizes, group=group, async_op=True)
+            if use_side:
+                send.record_stream(side)
         else:
             recv = win[u0:u_hi].view(-1)
             osz = [rows * (c1 - c0) if r == src else 0 for r in range(world)]
@@ -189,8 +204,8 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
     g_hi = S
     for j in reversed(range(len(chunks))):
         r0, r1 = chunks[j]
-        if arrive[j] is not None:
-            arrive[j].wait()                       # the compute stream waits; the host does not
+        if arrive[j] is not None and not is_src:
+            arrive[j].wait()                       # the compute stream waits; the host does not (src reads its own image)
         if xe > xb:
             compute_window(win, c0, T, travel_time_us, dist_km, vel, nearfield, xb, xe, block, (r0, r1, g_hi))
             g_hi = r0
@@ -206,18 +221,37 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
                                                  async_op=True)
     if not gather:
         return block
-    # ---- 3. rank src files the received rows into the image
-    for j in reversed(range(len(chunks))):
-        ship[j].wait()
-        if is_src:
-            r0, r1 = chunks[j]
-            off = 0
-            for r in range(world):
-                n = 0 if r == src else (r1 - r0) * (ranges[r][1] - ranges[r][0])
-                if n:
-                    out[r0:r1, ranges[r][0]:ranges[r][1]] = stages[j][off:off + n].view(r1 - r0, -1)
-                    off += n
+    # ---- 3. rank src files the received rows into the image (side stream: overlaps the kernels of later chunks)
+    with on_side():
+        for j in reversed(range(len(chunks))):
+            ship[j].wait()
+            if is_src:
+                r0, r1 = chunks[j]
+                off = 0
+                for r in range(world):
+                    n = 0 if r == src else (r1 - r0) * (ranges[r][1] - ranges[r][0])
+                    if n:
+                        out[r0:r1, ranges[r][0]:ranges[r][1]] = stages[j][off:off + n].view(r1 - r0, -1)
+                        off += n
+                if use_side:
+                    stages[j].record_stream(side)
+        for w in arrive.values():                  # src never waited for its sends on the compute stream
+            if w is not None and is_src:
+                w.wait()
+    if use_side:
+        main.wait_stream(side)
     return out
+
+
+_side_streams = {}
+
+
+def _side_stream(dev):
+    import torch
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
 
 
 def _spacing_is_uniform(travel_time_us, dist_km, vel):

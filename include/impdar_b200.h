@@ -247,8 +247,11 @@ int impdar_phsh_ffd_f64(const double *data, double *out, int snum, int tnum, dou
                         const double *vmig, const double *thr2, double htaper, double vtaper, void *workspace,
                         size_t workspace_bytes, void *stream);
 
-/* Testing hook: 1 selects the one-frequency-bin-per-state kernels instead of the (+w, -w) pair kernels. */
-int impdar_phsh_set_legacy(int on);
+/* Kernel selection of impdar_phsh_f32 (testing / A-B hook): 0 = automatic - constant velocity runs as a per-kx complex
+ * matrix product on the tensor cores (tcgen05.mma kind::tf32 with the 3xTF32 split, accumulators in TMEM, drained every
+ * stage; csrc/phaseshift_tc.cu), layered velocity on the (+w, -w) pair kernel; 1 = the first-generation
+ * one-bin-per-state SIMT kernels; 2 = same as 0; 3 = the SIMT pair kernels for both velocity models.              */
+int impdar_phsh_set_legacy(int mode);
 
 /* ------------------------------------ index / resampling operations (_RadarDataProcessing.py:20-637) --- */
 /* All bit-exact against the reference's numpy 2.3 / scipy 1.18 arithmetic (operation order, no FMA contraction).

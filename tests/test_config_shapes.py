@@ -229,3 +229,25 @@ def test_reference_cython_shim_links_against_the_library():
         sys.path.remove(ref)
         for k in [k for k in sys.modules if k == "impdar" or k.startswith("impdar.")]:
             del sys.modules[k]
+
+
+@pytest.mark.parametrize("S,T", [(256, 64), (300, 50), (1024, 256), (4096, 128), (5000, 40), (70, 33)])
+def test_phase_shift_const_tensor_core_vs_simt(S, T):
+    """Constant velocity: the tensor-core path (default; tcgen05 kind::tf32 with the 3xTF32 split and per-stage
+    accumulator drains) and the SIMT (+w, -w) pair kernel against the float64 oracle - pow-2 and padded nt, odd tnum,
+    nt < 64 (pair kernel only) and snum > 4096 (two accumulator passes)."""
+    import torch
+    from impdar_b200 import migrationlib as ml, _lib
+    from oracle import migration as om
+    lib = _lib.load()
+    d = synthetic_dat(S, T, seed=S + T)
+    x64 = d.data.astype(np.float64)
+    _, want = om.phase_shift(x64, d.dt, d.travel_time, d.trace_int, d.dist, VEL, 10, 10)
+    xd = torch.from_numpy(d.data).cuda()
+    for mode, name in ((0, "tensor-core"), (3, "simt pair")):
+        lib.impdar_phsh_set_legacy(mode)
+        try:
+            got = ml.phase_shift_device(xd, d.dt, 5.0, d.travel_time, VEL, 10, 10).double().cpu().numpy()
+        finally:
+            lib.impdar_phsh_set_legacy(0)
+        assert _report("phsh const %dx%d %s" % (S, T, name), got, want) < TOL
