@@ -26,7 +26,13 @@ constexpr int TC_M = 128;             // rows t0 of one accumulator pass: 128 x 
 constexpr int TC_B = 32;              // taus per row
 constexpr int TC_KC = 32;             // frequencies per stage
 constexpr int TC_NST = 2;             // stages
-constexpr int TC_GEN_WARPS = 8;       // warp w generates core-matrix column w (frequencies 4 w .. 4 w + 3 of the stage)
+#ifndef TC_CFG_GEN_WARPS
+#define TC_CFG_GEN_WARPS 8
+#endif
+constexpr int TC_GEN_WARPS = TC_CFG_GEN_WARPS;   // 8 or 16: warp w generates core-matrix column w % 8 (frequencies 4 c .. 4 c + 3 of
+                                                 // the stage); with 16 warps the rows of a column are split between two warps
+constexpr int TC_HALVES = TC_GEN_WARPS / 8;
+static_assert(TC_GEN_WARPS == 8 || TC_GEN_WARPS == 16, "8 or 16 generator warps");
 constexpr int TC_MMA_WARP = TC_GEN_WARPS;          // one elected thread issues the MMAs
 constexpr int TC_DRAIN_WARP0 = TC_GEN_WARPS + 1;   // four warps drain the accumulators (TMEM lane quarter = warp % 4)
 constexpr int TC_THREADS = (TC_GEN_WARPS + 5) * 32;
@@ -197,30 +203,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) phsh_const_tc_kernel(const __gr
         if (warp < TC_GEN_WARPS) {
             // ------------------------------------------------------------------ generators
             const int r = lane >> 2, kq = lane & 3;        // row within a core matrix, frequency within the 16-byte chunk
-            const int kk = 4 * warp + kq;                  // frequency within the stage
+            const int cc = warp & 7, half = warp >> 3;     // core-matrix column of this warp, and which part of its rows
+            const int kk = 4 * cc + kq;                    // frequency within the stage
             const int groups = min(TC_M / 8, (rows_needed - t0_base + 7) / 8);   // 8-row groups with real taus
+            const int ia0 = half * (TC_M / 8 / TC_HALVES), ia1 = min(groups, ia0 + TC_M / 8 / TC_HALVES);
+            const int ib0 = half * (4 / TC_HALVES), ib1 = ib0 + 4 / TC_HALVES;
+            // phase and spectrum value of this thread's frequency, fetched one stage ahead (the FK column is strided: L2 latency)
+            auto fetch = [&](int s, double &u, float2 &fk) {
+                const int pidx = s * TC_KC + kk;
+                fk = make_float2(0.f, 0.f);
+                u = 0.0;
+                if (s < n_stage && pidx < n_list) {
+                    const int iw = (pidx < n_pos) ? smin + pidx : nh + 1 + (pidx - n_pos);
+                    u = p.turns[(size_t)k * p.nt + iw];
+                    fk = p.FK[(size_t)iw * p.K + k];
+                }
+            };
+            double u_next;
+            float2 fk_next;
+            fetch(0, u_next, fk_next);
             for (int s = 0; s < n_stage; ++s, ++it) {
                 const int slot = it % TC_NST;
+                double u = u_next;
+                float2 fk = fk_next;
+                fetch(s + 1, u_next, fk_next);
+                if (!(u > -1.5)) {                         // (every listed bin propagates; the evanescent marker is a guard)
+                    u = 0.0;
+                    fk = make_float2(0.f, 0.f);
+                }
                 if (it >= TC_NST) tc_mbar_wait(&empty[slot], (unsigned)((it / TC_NST - 1) & 1));
                 float *sa = stage0 + (size_t)slot * TC_STAGE_FLOATS;
                 float *a_re_hi = sa, *a_re_lo = sa + TC_A_FLOATS, *a_im_hi = sa + 2 * TC_A_FLOATS, *a_im_lo = sa + 3 * TC_A_FLOATS;
                 float *sb = sa + 4 * TC_A_FLOATS;
                 float *b1_hi = sb, *b1_lo = sb + TC_B_FLOATS, *b2_hi = sb + 2 * TC_B_FLOATS, *b2_lo = sb + 3 * TC_B_FLOATS;
-                const int pidx = s * TC_KC + kk;
-                float2 fk = make_float2(0.f, 0.f);
-                double u = 0.0;
-                if (pidx < n_list) {
-                    const int iw = (pidx < n_pos) ? smin + pidx : nh + 1 + (pidx - n_pos);
-                    u = p.turns[(size_t)k * p.nt + iw];
-                    if (u > -1.5) fk = p.FK[(size_t)iw * p.K + k];   // (every listed bin propagates; the marker is a guard)
-                    else u = 0.0;
-                }
                 // A: rows t0 = t0_base + 8 i + r  ->  FK (z^32)^t0 ; seed at i = 0, then multiply by (z^32)^8
                 {
-                    float2 a = tc_cmul(fk, tc_cis(u, TC_B * (t0_base + r)));
+                    float2 a = tc_cmul(fk, tc_cis(u, TC_B * (t0_base + 8 * ia0 + r)));
                     const float2 step = tc_cis(u, TC_B * 8);
-                    const int base = (warp * (TC_M / 8)) * 32 + r * 4 + kq;
-                    for (int i = 0; i < groups; ++i) {
+                    const int base = (cc * (TC_M / 8)) * 32 + r * 4 + kq;
+                    for (int i = ia0; i < ia1; ++i) {
                         float h, l;
                         tc_split(a.x, h, l);
                         a_re_hi[base + i * 32] = h;
@@ -233,11 +254,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) phsh_const_tc_kernel(const __gr
                 }
                 // B: rows n = 8 i + r (i < 4) hold z^(n + 1): [B_re | B_im] and [-B_im | B_re]
                 {
-                    float2 b = tc_cis(u, r + 1);
+                    float2 b = tc_cis(u, 8 * ib0 + r + 1);
                     const float2 step = tc_cis(u, 8);
-                    const int base = (warp * 8) * 32 + r * 4 + kq;
+                    const int base = (cc * 8) * 32 + r * 4 + kq;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = ib0; i < ib1; ++i) {
                         float h, l;
                         tc_split(b.x, h, l);
                         b1_hi[base + i * 32] = h;           // rows 0..31: re
@@ -305,31 +326,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) phsh_const_tc_kernel(const __gr
                 const int acc = (ig + g) & 1;
                 tc_mbar_wait(&tfull[acc], (unsigned)(((ig + g) >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                unsigned v[64];
                 const unsigned taddr = tmem_d + 64u * (unsigned)acc + ((unsigned)(32 * q) << 16);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
-                      "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
-                      "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
-                      "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
-                    : "r"(taddr + 32u));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c16 = 0; c16 < 4; ++c16) {
+                    unsigned v[16];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                        : "r"(taddr + 16u * (unsigned)c16));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[16 * c16 + j] += __uint_as_float(v[j]);
+                }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive(&tempty[acc]);          // the accumulator may be overwritten
-#pragma unroll
-                for (int j = 0; j < 64; ++j) sum[j] += __uint_as_float(v[j]);
             }
+
 #pragma unroll
             for (int j = 0; j < TC_B; ++j) {
                 const int tau = TC_B * t0 + j;

@@ -251,3 +251,37 @@ def test_phase_shift_const_tensor_core_vs_simt(S, T):
         finally:
             lib.impdar_phsh_set_legacy(0)
         assert _report("phsh const %dx%d %s" % (S, T, name), got, want) < TOL
+
+
+def test_kirchhoff_tile_kernel_is_deterministic_and_used():
+    """The shared-memory tile kernel is a producer / consumer pipeline over mbarriers (TMA writes, consumer reads,
+    slot reuse) - a hazard compute-sanitizer's racecheck cannot model (it reports every TMA write / consumer read pair
+    across the mbarriers, profiles/r02g_sanitizer_racecheck.txt).  A real race would show as run-to-run differences:
+    five runs of the config-2 shape must agree bit for bit, with each other and with the image assembled from row
+    chunks and trace ranges (different CTA decompositions of the same sums)."""
+    import torch
+    from impdar_b200 import migrationlib as ml
+    S, T = 2048, 4096
+    x = _noise(S, T, 41)
+    tt, dist = _geometry(S, T)
+    first = ml.kirchhoff_device(x, tt, dist, VEL, False)
+    assert ml.kirchhoff_last_kernel() == "table_tile"
+    for _ in range(4):
+        assert torch.equal(ml.kirchhoff_device(x, tt, dist, VEL, False), first)
+    parts = []
+    for xb, xe in ((0, 1000), (1000, 1001), (1001, 3000), (3000, T)):
+        block = torch.empty((S, xe - xb), dtype=torch.float32, device="cuda")
+        g_hi = S
+        for r0, r1 in ((1500, S), (700, 1500), (3, 700), (0, 3)):
+            ml.kirchhoff_rows_device(x, tt, dist, VEL, False, xb, xe, r0, r1, g_hi, block)
+            g_hi = r0
+        parts.append(block)
+    assert torch.equal(torch.cat(parts, dim=1), first)
+    ml.set_kirchhoff_mode(ml.KIRCHHOFF_TABLE_GATHER)
+    try:
+        gather = ml.kirchhoff_device(x, tt, dist, VEL, False)
+        assert ml.kirchhoff_last_kernel() == "table_gather"
+    finally:
+        ml.set_kirchhoff_mode(ml.KIRCHHOFF_AUTO)
+    # same picks and weights, different summation order: equal to float32 rounding, not bit for bit
+    assert float((gather - first).abs().max()) <= 2e-5 * float(first.abs().max())
