@@ -158,6 +158,16 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
     dev, dt = x.device, x.dtype
     empty = torch.empty(0, dtype=dt, device=dev)
     is_src = rank == src
+    import os
+    trace = [] if (os.environ.get("IMPDAR_TRACE_SHARDED") and x.is_cuda) else None
+
+    def mark(label):
+        if trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            trace.append((label, ev))
+
+    mark("start")
     # ---- 1. input windows, every chunk enqueued up front (the collective stream runs them back to back).  On `src` the
     # packing of the other ranks' column slabs and, later, the filing of their finished rows run on a side stream: the
     # compute stream of `src` only ever waits for the kernels of its own range.
@@ -206,9 +216,11 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
         r0, r1 = chunks[j]
         if arrive[j] is not None and not is_src:
             arrive[j].wait()                       # the compute stream waits; the host does not (src reads its own image)
+        mark("window %d here" % j)
         if xe > xb:
             compute_window(win, c0, T, travel_time_us, dist_km, vel, nearfield, xb, xe, block, (r0, r1, g_hi))
             g_hi = r0
+        mark("chunk %d computed" % j)
         if gather:
             rows = r1 - r0
             if is_src:
@@ -240,6 +252,11 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
                 w.wait()
     if use_side:
         main.wait_stream(side)
+    mark("image assembled")
+    if trace is not None:
+        torch.cuda.synchronize()
+        print("[rank %d] " % rank + "  ".join("%s %.2f" % (lab, trace[0][1].elapsed_time(ev)) for lab, ev in trace[1:]),
+              flush=True)
     return out
 
 
