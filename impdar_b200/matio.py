@@ -102,6 +102,15 @@ def check_attrs(dat):
         dat.data_dtype = dat.data.dtype
 
 
+def _struct_to_plain(v):
+    """A MATLAB struct as scipy.io.loadmat returns it ((1, 1) structured array) -> nested dicts of its fields, which
+    scipy.io.savemat writes back as the same struct (writing the structured array itself would box every field once
+    more).  load -> save -> load is then the identity on the struct, however often it is repeated."""
+    if isinstance(v, np.ndarray) and v.dtype.names:
+        return {n: _struct_to_plain(v[n][0, 0]) for n in v.dtype.names}
+    return v
+
+
 def load_mat(fn_mat, pinned=True):
     """Read a StoDeep / ImpDAR .mat file into an impdar_b200.RadarData; mirrors RadarData/__init__.py:207-244
     (KeyError for files that are not in the format, ImpdarError for inconsistent ones)."""
@@ -167,7 +176,7 @@ def save(self, fn):
         except Exception:
             ok = False
         if ok:
-            mat['picks'] = picks_struct
+            mat['picks'] = _struct_to_plain(picks_struct)
         else:
             import warnings
             warnings.warn('%s: the picks loaded with this file no longer match the radargram (the trace or sample axis '
