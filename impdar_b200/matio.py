@@ -166,16 +166,21 @@ def save(self, fn):
         # arrays still match the radargram; after a step that changed the trace or sample axis they are stale, and
         # dropping them silently would lose data without a trace - warn loudly instead.
         ok = True
+        has_picks = True
         try:
             samp = picks_struct['samp1'][0, 0]
+            # an unpicked profile carries the placeholder the reference writes for None (a scalar 0): nothing to keep
+            has_picks = samp.size > 1 or (samp.size == 1 and samp.ravel()[0] != 0)
             tnum = int(np.shape(mat['data'])[1])
-            ok = samp.size == 0 or samp.ndim < 2 or samp.shape[1] == tnum
+            ok = samp.ndim < 2 or samp.shape[1] == tnum
             loaded = getattr(self, '_picks_axes', None)
             if loaded is not None and loaded != (int(np.shape(mat['data'])[0]), tnum):
                 ok = False
         except Exception:
             ok = False
-        if ok:
+        if not has_picks:
+            pass
+        elif ok:
             mat['picks'] = _struct_to_plain(picks_struct)
         else:
             import warnings
