@@ -43,6 +43,14 @@ void ktimer_end(cudaStream_t st);
         }                                                                                    \
     } while (0)
 
+// Function attributes (dynamic shared-memory limits) are per device: cache "already set" per device index, not per process.
+constexpr int IMPDAR_MAX_DEVICES = 64;
+static inline int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < IMPDAR_MAX_DEVICES) ? dev : 0;
+}
+
 static inline int num_sms() {
     static int sms = 0;
     if (!sms) {

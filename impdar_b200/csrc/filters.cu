@@ -758,7 +758,8 @@ static int launch_ahfilt_slide(const T *x, T *y, int S, int Tn, int batch, int w
     const int nstrips = (Tn + WS - 1) / WS;
     const int nw = nstrips < 8 ? nstrips : 8;
     const size_t smem = (size_t)nw * 7 * WS * sizeof(T);
-    static bool attr_done = false;
+    static bool attr_done_dev[IMPDAR_MAX_DEVICES];
+    bool &attr_done = attr_done_dev[current_device_slot()];
     if (!attr_done) {
         if (8 * 7 * WS * sizeof(T) > 48 * 1024)
             IMPDAR_CUDA(cudaFuncSetAttribute(ahfilt_slide_kernel<T, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1060,7 +1061,8 @@ static int ahfilt_impl(const T *x, T *y, int S, int Tn, int batch, int w, const 
             return IMPDAR_B200_OK;
         }
         if (nmax <= 4096) {
-            static bool attr_done = false;
+            static bool attr_done_dev[IMPDAR_MAX_DEVICES];
+            bool &attr_done = attr_done_dev[current_device_slot()];
             if (!attr_done) {
                 IMPDAR_CUDA(cudaFuncSetAttribute(ahfilt_strip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
                 attr_done = true;

@@ -791,10 +791,11 @@ static int get_tables(int S, int T, cudaStream_t st, Tables &out) {
 template <int N1, int DIR>
 static int launch_rowA(const RowAParams &p, cudaStream_t st) {
     const size_t smem = (size_t)(2 * TILE_A + N1 * NC2 + N1) * sizeof(cf);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[IMPDAR_MAX_DEVICES];
+    const int dev = current_device_slot();
+    if (!attr_done[dev]) {
         IMPDAR_CUDA(cudaFuncSetAttribute(stolt_rowA_kernel<N1, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        attr_done[dev] = true;
     }
     dim3 grid(N2 / NC2, (p.S + p.rows_per_cta - 1) / p.rows_per_cta, p.batch);
     ktimer_begin("stolt_rowA_kernel", st);
@@ -820,11 +821,12 @@ static int dispatch_rowA(const RowAParams &p, cudaStream_t st) {
 template <int DIR>
 static int launch_rowB(const RowBParams &p, cudaStream_t st) {
     const size_t smem = (size_t)(RB_TILE + 512) * sizeof(cf);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[IMPDAR_MAX_DEVICES];
+    const int dev = current_device_slot();
+    if (!attr_done[dev]) {
         IMPDAR_CUDA(cudaFuncSetAttribute(stolt_rowB_kernel<DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IMPDAR_CUDA(cudaFuncSetAttribute(stolt_rowB_self_kernel<DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        attr_done[dev] = true;
     }
     dim3 grid(p.N1 / 2 - 1, p.S / 16, p.batch);
     ktimer_begin("stolt_rowB_kernel", st);
@@ -843,7 +845,8 @@ template <int S, int R3, bool PF>
 static int launch_col(const ColParams &p, cudaStream_t st) {
     constexpr int NT = S / 32;
     const size_t smem = (size_t)(S + S / 16 + 512) * sizeof(cf) + 16;  // + the mbarrier
-    static int ctas_per_sm = 0;
+    static int ctas_per_sm_dev[IMPDAR_MAX_DEVICES];
+    int &ctas_per_sm = ctas_per_sm_dev[current_device_slot()];
     if (!ctas_per_sm) {
         IMPDAR_CUDA(cudaFuncSetAttribute(stolt_col_kernel<S, R3, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int n = 0;

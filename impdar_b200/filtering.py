@@ -386,8 +386,12 @@ def rangegain(self, slope):
         out = rowgain_device(x, suffix, gain, None, True)
     else:
         trig = np.asarray(self.trig).astype(int).flatten()
-        # per-trace trigger: data[int(trig) + 1:, i] *= travel_time[int(trig) + 1:] * slope
-        out = rowgain_device(x, suffix, tt * slope, trig, True)
+        # per-trace trigger: data[int(trig) + 1:, i] *= travel_time[int(trig) + 1:] * slope.  The slice start follows
+        # Python's rules: trig + 1 < 0 counts from the end (negative triggers occur after crop(..., zero_trig=False)).
+        # The kernel applies the gain to rows s > trig'[i]; trig' = start - 1 with the start resolved here.
+        start = trig + 1
+        start = np.where(start < 0, np.maximum(self.snum + start, 0), start)
+        out = rowgain_device(x, suffix, tt * slope, (start - 1).astype(np.int32), True)
     _unstage(self, out, np_dtype, was_device)
     self.flags.rgain = True
 

@@ -424,3 +424,18 @@ def test_tk_float64_is_exact_and_device_dtypes_never_narrow():
         d.data = torch.from_numpy(d.data).cuda()
         d.migrate(mtype=mtype)
         assert d.data.is_cuda and d.data.dtype == torch.float32, mtype
+
+
+def test_rangegain_negative_per_trace_triggers():
+    """Per-trace triggers below -1 (they occur after crop(..., zero_trig=False)): the reference slices
+    data[int(trig) + 1:, i] with Python's negative-index rules (_RadarDataProcessing.py:466-469), so only the last rows
+    get the gain."""
+    d = synthetic_dat(40, 12, seed=9, dtype=np.float64)
+    trig = np.array([3, -1, -2, -5, 0, -40, -41, -100, 38, 39, 45, -3])
+    d.trig = trig.copy()
+    want = d.data.copy()
+    for i, t in enumerate(trig):                                   # the reference's own loop
+        gain = d.travel_time[int(t) + 1:] * 0.3
+        want[int(t) + 1:, i] *= gain
+    d.rangegain(0.3)
+    assert np.array_equal(d.data, want)
