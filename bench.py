@@ -187,6 +187,8 @@ class Workload(object):
             if isinstance(self.__dict__[k], torch.Tensor):
                 del self.__dict__[k]
         device.free_workspaces()
+        from impdar_b200 import parallel
+        parallel.free_exchange_buffers()
         torch.cuda.empty_cache()
 
 
@@ -352,8 +354,8 @@ class KirchhoffC2(Workload):
 
 
 class KirchhoffC5(KirchhoffC2):
-    """configs[4] = the north-star target: ONE radargram of 65536 traces x 8192 samples.  N ranks: output-trace ranges
-    balanced by pair count, every rank receives only the input columns its range can reach (range + one aperture
+    """configs[4] = the north-star target: ONE radargram of 65536 traces x 8192 samples.  N ranks: equal output-trace
+    ranges, every rank receives only the input columns its range can reach (range + one aperture
     each side) from the rank that holds the radargram, and the (snum, range) output blocks are gathered straight into
     the final image - both exchanges inside the timed step, overlapped with the kernels in bottom-up row chunks."""
     name = "kirchhoff_65536tr_x_8192smp"
@@ -370,6 +372,10 @@ class KirchhoffC5(KirchhoffC2):
     def parallelism(self):
         if self.world == 1:
             return "one GPU, whole image"
+        if self.parallel.peer_output_active():
+            return ("equal output-trace ranges per GPU; in the timed step: NCCL halo send/recv of the input columns, and the "
+                    "diffraction-sum kernels store their output blocks straight into rank 0's image through peer-mapped "
+                    "memory (CUDA IPC over NVLink), one-element all_reduce per row chunk as completion signal")
         return "output-trace ranges per GPU; NCCL halo send/recv of the input columns + gather of the output blocks in the timed step"
 
     def setup(self):
@@ -397,8 +403,9 @@ class KirchhoffC5(KirchhoffC2):
 
     def step(self):
         kw = {}
-        if os.environ.get("IMPDAR_C5_CHUNKS"):          # development A/B switch for the exchange pipeline depth
-            kw["pipeline_chunks"] = int(os.environ["IMPDAR_C5_CHUNKS"])
+        if os.environ.get("IMPDAR_C5_CHUNKS"):          # development A/B switch for the exchange pipeline: "4" or "1,2,2,1"
+            c = os.environ["IMPDAR_C5_CHUNKS"]
+            kw["pipeline_chunks"] = [float(v) for v in c.split(",")] if "," in c else int(c)
         self.result = None
         self.result = self.parallel.kirchhoff_sharded_device(
             self.x, self.tt, self.dist, VEL_K, False, rank=self.rank, world=self.world,
@@ -444,8 +451,10 @@ class KirchhoffC5(KirchhoffC2):
     def roofline(self, ms, hbm_gbs, src):
         r = kirchhoff_roofline(self, ms, hbm_gbs, src, self.pairs_rank, self.pairs, self.exact_pairs)
         if self.world > 1:
-            r["note"] = ("achieved/peak are per GPU (rank 0's kernel and rank 0's share of the pairs; ranges are balanced "
-                         "by pair count); the step adds the exposed part of the halo exchange and of the output gather")
+            r["note"] = ("achieved/peak are per GPU (rank 0's kernel and rank 0's share of the pairs; every rank owns the "
+                         "same number of output traces - the table kernels' cost is per trace - so the end ranks, whose "
+                         "apertures are cut by the profile ends, count fewer pairs for the same work); the step adds the "
+                         "exposed part of the halo exchange")
         return r
 
     def parity(self):

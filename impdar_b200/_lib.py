@@ -61,6 +61,11 @@ PROTOTYPES = {
     "impdar_kirchhoff_last_stats": (_c_int, [_vp, _vp]),
     "impdar_kirchhoff_set_mode": (_c_int, [_c_int]),
     "impdar_kirchhoff_last_path": (_c_int, []),
+    "impdar_peer_alloc": (_c_int, [_c_sz, _vp, _vp]),
+    "impdar_peer_free": (_c_int, [_vp]),
+    "impdar_peer_open": (_c_int, [_vp, _vp]),
+    "impdar_peer_close": (_c_int, [_vp]),
+    "impdar_copy2d_f32": (_c_int, [_vp, _c_sz, _vp, _c_sz, _c_int, _c_int, _vp]),
     "mig_kirch_loop": (None, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _vp, _c_dbl, _c_int]),
     "impdar_kirchhoff_host_f64": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp, _c_dbl, _c_int]),
     "impdar_stolt_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int]),

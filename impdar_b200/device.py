@@ -27,7 +27,7 @@ def ptr(t):
     """Device (or host) address of a tensor / numpy array as c_void_p; None -> NULL."""
     if t is None:
         return ctypes.c_void_p(0)
-    if isinstance(t, torch.Tensor):
+    if hasattr(t, "data_ptr"):                  # torch tensors and raw-address blocks (parallel._RawBlock)
         return ctypes.c_void_p(t.data_ptr())
     return ctypes.c_void_p(t.ctypes.data)
 

@@ -10,6 +10,12 @@
 import numpy as np
 
 
+# Row chunks of the exchange pipeline, relative heights top to bottom.  The bottom chunk is the first window to arrive
+# (nothing can start before it) and the top chunk's rows are the last to reach the image: both small; measured at 8 GPUs
+# on 65536 x 8192 (profiles/r02m_exchange_variants_n8.txt): 4 equal chunks 36.3 ms, (1, 2, 2, 2, 1) 29.7, this 29.4.
+DEFAULT_CHUNKS = (1, 2, 3, 3, 2, 1)
+
+
 def profiles_for_rank(n_profiles, rank, world):
     """Indices of the profiles rank `rank` owns (p mod world == rank, process.py:151-193's serial loop split)."""
     return list(range(rank, n_profiles, world))
@@ -45,22 +51,31 @@ _range_cache = {}
 
 
 def kirchhoff_output_ranges(tnum, world, travel_time_us, dist_km, vel, align=8):
-    """[(x_begin, x_end)] per rank: contiguous, covering [0, tnum), balanced by pair count, boundaries
-    aligned to the kernel's 8-trace CTA tile."""
+    """[(x_begin, x_end)] per rank: contiguous, covering [0, tnum).  Uniform trace spacing (the table path): equal
+    trace counts; any other geometry (the general kernel, which loops over the exact aperture): balanced by pair count,
+    boundaries aligned to the kernel's 8-trace CTA tile."""
     tt = np.ascontiguousarray(travel_time_us, dtype=np.float64)
     dk = np.ascontiguousarray(dist_km, dtype=np.float64)
     key = (int(tnum), int(world), float(vel), int(align), hash(tt.tobytes()), hash(dk.tobytes()))
     hit = _range_cache.get(key)
     if hit is not None:
         return list(hit)
-    cost = kirchhoff_trace_cost(tt, dk, vel)
-    cum = np.concatenate([[0.0], np.cumsum(cost)])
-    bounds = [0]
-    for r in range(1, world):
-        x = int(np.searchsorted(cum, cum[-1] * r / world))
-        x = int(round(x / align)) * align
-        x = min(max(x, bounds[-1]), tnum)
-        bounds.append(x)
+    if _spacing_is_uniform(tt, dk, vel):
+        # table / tile kernels (uniform trace spacing): every output trace walks the same table rows - traces near
+        # the ends of the profile sum zero padding instead of skipping it - so the cost is per TRACE, not per pair;
+        # whole 256-trace CTA tiles per rank where the ranges are wide enough for that not to unbalance them
+        tile = 256 if tnum >= 8 * 256 * world else align
+        bounds = [min(int(round(tnum * r / world / tile)) * tile, tnum) for r in range(world)]
+        bounds = [max(b, 0) for b in np.maximum.accumulate(bounds)]
+    else:
+        cost = kirchhoff_trace_cost(tt, dk, vel)
+        cum = np.concatenate([[0.0], np.cumsum(cost)])
+        bounds = [0]
+        for r in range(1, world):
+            x = int(np.searchsorted(cum, cum[-1] * r / world))
+            x = int(round(x / align)) * align
+            x = min(max(x, bounds[-1]), tnum)
+            bounds.append(x)
     bounds.append(tnum)
     ranges = [(bounds[r], bounds[r + 1]) for r in range(world)]
     if len(_range_cache) > 64:
@@ -74,7 +89,15 @@ def kirchhoff_output_range(tnum, rank, world, travel_time_us, dist_km, vel):
 
 
 def row_chunks(snum, nchunks):
-    """[(r0, r1)] of the bottom-up row pipeline, listed top-down (chunk j = rows [snum j / n, snum (j+1) / n))."""
+    """[(r0, r1)] of the bottom-up row pipeline, listed top-down.  `nchunks` is a count (chunk j = rows
+    [snum j / n, snum (j+1) / n)) or a sequence of relative chunk heights, top to bottom (e.g. (1, 2, 2, 1): the first
+    window to arrive and the last rows to ship are half-size chunks)."""
+    if hasattr(nchunks, "__len__"):
+        w = np.asarray(nchunks, dtype=np.float64)
+        b = np.concatenate([[0.0], np.cumsum(w)]) / w.sum() * snum
+        b = np.round(b).astype(int)
+        b[0], b[-1] = 0, snum
+        return [(int(b[j]), int(b[j + 1])) for j in range(len(w)) if b[j + 1] > b[j]]
     n = max(1, min(int(nchunks), int(snum)))
     return [(snum * j // n, snum * (j + 1) // n) for j in range(n)]
 
@@ -142,13 +165,16 @@ def kirchhoff_input_windows(snum, tnum, ranges, travel_time_us, dist_km, vel, wi
 
 
 def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, world, group, src, ranges, windows,
-                            nchunks, compute_window, gather):
+                            nchunks, compute_window, gather, peer=None):
     """Halo exchange: rank `src` holds the radargram; every other rank receives ONLY the columns its output range can
     read (its window), bottom-up in row chunks, computes each chunk of its range as soon as the rows are there and
     ships the finished rows to `src` (gather == 'src') while the next chunk runs.  Both exchanges are one
     all_to_all_single per chunk with empty splits everywhere except from / to `src`.  Rank `src` computes straight
-    from its own image into the final one.  Returns the (snum, tnum) image on `src` (None elsewhere) for
-    gather == 'src', or this rank's (snum, range) block for gather False."""
+    from its own image into the final one.  With `peer` (a _PeerImage: rank src's persistent image mapped into every
+    rank) nothing is shipped at all: the kernels of the other ranks store their blocks into src's memory over NVLink
+    as they run, a one-element all_reduce per chunk tells src that the chunk's rows are complete everywhere, and src
+    copies them into the image it returns on its side stream.  Returns the (snum, tnum) image on `src` (None
+    elsewhere) for gather == 'src', or this rank's (snum, range) block for gather False."""
     import torch
     import torch.distributed as dist
     S, T = x.shape
@@ -181,7 +207,7 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
         import contextlib
         return torch.cuda.stream(side) if use_side else contextlib.nullcontext()
 
-    win = x[:, c0:c1] if is_src else torch.empty((S, c1 - c0), dtype=dt, device=dev)
+    win = x[:, c0:c1] if is_src else _halo_buffer("win", (S, c1 - c0), dt, dev)
     arrive = {}
     u_hi = S
     for j in reversed(range(len(chunks))):
@@ -193,23 +219,29 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
         if is_src:
             sizes = [0 if r == src else rows * (windows[r][1] - windows[r][0]) for r in range(world)]
             with on_side():
-                send = torch.empty(sum(sizes), dtype=dt, device=dev)
+                send = _halo_buffer(("send", j), (sum(sizes),), dt, dev)
                 off = 0
                 for r in range(world):
                     if sizes[r]:
                         send[off:off + sizes[r]].view(rows, -1).copy_(x[u0:u_hi, windows[r][0]:windows[r][1]])
                         off += sizes[r]
                 arrive[j] = dist.all_to_all_single(empty, send, [0] * world, sizes, group=group, async_op=True)
-            if use_side:
-                send.record_stream(side)
         else:
             recv = win[u0:u_hi].view(-1)
             osz = [rows * (c1 - c0) if r == src else 0 for r in range(world)]
             arrive[j] = dist.all_to_all_single(recv, empty, osz, [0] * world, group=group, async_op=True)
         u_hi = u0
     # ---- 2. chunk by chunk: wait for its rows, compute, ship the finished rows
+    use_peer = peer is not None and bool(gather)
     out = torch.empty((S, T), dtype=dt, device=dev) if (is_src and gather) else None
-    block = out[:, xb:xe] if out is not None else torch.empty((S, max(xe - xb, 0)), dtype=dt, device=dev)
+    if out is not None:
+        block = out[:, xb:xe]
+    elif use_peer:
+        block = peer.block(xb, xe)                 # this rank's columns of src's image, through the peer mapping
+    elif gather:
+        block = _halo_buffer("block", (S, max(xe - xb, 0)), dt, dev)
+    else:
+        block = torch.empty((S, max(xe - xb, 0)), dtype=dt, device=dev)
     ship, stages = {}, {}
     g_hi = S
     for j in reversed(range(len(chunks))):
@@ -221,11 +253,14 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
             compute_window(win, c0, T, travel_time_us, dist_km, vel, nearfield, xb, xe, block, (r0, r1, g_hi))
             g_hi = r0
         mark("chunk %d computed" % j)
-        if gather:
+        if use_peer:
+            # stream order: this rank's kernels of chunk j (and their peer stores) are complete before it joins
+            ship[j] = dist.all_reduce(_halo_buffer(("done", j), (1,), dt, dev, zero=True), group=group, async_op=True)
+        elif gather:
             rows = r1 - r0
             if is_src:
                 sizes = [0 if r == src else rows * (ranges[r][1] - ranges[r][0]) for r in range(world)]
-                stages[j] = torch.empty(sum(sizes), dtype=dt, device=dev)
+                stages[j] = _halo_buffer(("stage", j), (sum(sizes),), dt, dev)
                 ship[j] = dist.all_to_all_single(stages[j], empty, sizes, [0] * world, group=group, async_op=True)
             else:
                 isz = [rows * (xe - xb) if r == src else 0 for r in range(world)]
@@ -237,7 +272,12 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
     with on_side():
         for j in reversed(range(len(chunks))):
             ship[j].wait()
-            if is_src:
+            if is_src and use_peer:
+                r0, r1 = chunks[j]
+                for a, b in ((0, xb), (xe, T)):    # the other ranks' columns, either side of this rank's own
+                    if b > a:
+                        peer.copy_rows_to(out, r0, r1, a, b)
+            elif is_src:
                 r0, r1 = chunks[j]
                 off = 0
                 for r in range(world):
@@ -245,8 +285,6 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
                     if n:
                         out[r0:r1, ranges[r][0]:ranges[r][1]] = stages[j][off:off + n].view(r1 - r0, -1)
                         off += n
-                if use_side:
-                    stages[j].record_stream(side)
         for w in arrive.values():                  # src never waited for its sends on the compute stream
             if w is not None and is_src:
                 w.wait()
@@ -260,7 +298,155 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
     return out
 
 
+class _RawBlock(object):
+    """A (rows, cols) float32 block at a raw device address with row stride `ld` - a region of a peer-mapped image:
+    what kirchhoff_window_device needs of its `out` argument."""
+
+    def __init__(self, address, shape, ld):
+        self.address, self.shape, self.ld = int(address), tuple(shape), int(ld)
+
+    def data_ptr(self):
+        return self.address
+
+    def stride(self, i):
+        return (self.ld, 1)[i]
+
+
+class _PeerImage(object):
+    """One persistent (snum, tnum) float32 image in the memory of rank `src`, mapped into the address space of every
+    other rank of the node (csrc/peer.cu: cudaMalloc + CUDA IPC, peer access over NVLink / NVSwitch).  The other
+    ranks' diffraction-sum kernels store their output blocks straight into it while they run; rank `src` copies the
+    finished rows into the image it returns (a side-stream copy per row chunk), so the caller owns its result as with
+    the unsharded call.  Building one is a collective over `group` (once per image shape); `ok` is the same on every
+    rank."""
+
+    def __init__(self, S, T, rank, src, world, group, dev):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        lib = _lib.load()
+        self.S, self.T, self.src, self.is_src, self.lib = S, T, src, rank == src, lib
+        self.address = 0
+        good = 1
+        handle = torch.zeros(64, dtype=torch.uint8, device=dev)
+        if self.is_src:
+            h = (ctypes.c_ubyte * 64)()
+            p = ctypes.c_void_p(0)
+            if lib.impdar_peer_alloc(ctypes.c_size_t(S * T * 4), ctypes.byref(p), h) == 0:
+                self.address = int(p.value)
+                handle.copy_(torch.frombuffer(bytearray(h), dtype=torch.uint8))
+            else:
+                good = 0
+        dist.broadcast(handle, src=src, group=group)
+        if not self.is_src:
+            h = (ctypes.c_ubyte * 64).from_buffer_copy(bytes(handle.cpu().numpy().tobytes()))
+            p = ctypes.c_void_p(0)
+            if lib.impdar_peer_open(h, ctypes.byref(p)) == 0:
+                self.address = int(p.value)
+            else:
+                good = 0
+        flag = torch.tensor([good], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.ok = bool(int(flag.item()))
+
+    def block(self, xb, xe):
+        """Columns [xb, xe) of the image as the `out` of kirchhoff_window_device (any rank)."""
+        return _RawBlock(self.address + 4 * xb, (self.S, xe - xb), self.T)
+
+    def copy_rows_to(self, out, r0, r1, c0, c1):
+        """out[r0:r1, c0:c1] = image[r0:r1, c0:c1] on the current stream (rank src)."""
+        import ctypes
+        from . import _lib, device
+        if r1 <= r0 or c1 <= c0:
+            return
+        off = 4 * (r0 * self.T + c0)
+        dst = out.data_ptr() + out.element_size() * (r0 * out.stride(0) + c0)
+        _lib.check(self.lib.impdar_copy2d_f32(ctypes.c_void_p(self.address + off), self.T, ctypes.c_void_p(dst),
+                                              int(out.stride(0)), r1 - r0, c1 - c0, device.current_stream_ptr()))
+
+    def close(self):
+        import ctypes
+        if self.address and not self.is_src:
+            self.lib.impdar_peer_close(ctypes.c_void_p(self.address))
+            self.address = 0
+
+    def free(self):
+        import ctypes
+        if self.address and self.is_src:
+            self.lib.impdar_peer_free(ctypes.c_void_p(self.address))
+            self.address = 0
+
+
+_peer_images = {}
+
+
+def _peer_image(S, T, rank, src, world, group, dev):
+    """The cached peer-mapped image for this shape, or None when peer mapping is switched off (IMPDAR_PEER_OUTPUT=0)
+    or did not work on some rank (the halo exchange then ships the rows with all_to_all as before).  Every rank takes
+    the same decision: the environment switch is reduced over the group with the mapping outcome."""
+    import os
+    key = (S, T, src, world, id(group) if group is not None else None, str(dev))
+    if key not in _peer_images:
+        if os.environ.get("IMPDAR_PEER_OUTPUT", "1") == "0":
+            _peer_images[key] = None
+        else:
+            try:
+                img = _PeerImage(S, T, rank, src, world, group, dev)
+            except (RuntimeError, OSError, AttributeError) as e:      # collective state is unknown: do not retry
+                import warnings
+                warnings.warn("impdar_b200: peer-mapped output image unavailable (%s); using the all_to_all gather" % e)
+                img = None
+            if img is not None and not img.ok:
+                img.close()
+                img.free()
+                img = None
+            _peer_images[key] = img
+    return _peer_images[key]
+
+
 _side_streams = {}
+_halo_buffers = {}
+
+
+def _halo_buffer(key, shape, dtype, device, zero=False):
+    """Persistent exchange buffers (send slabs, receive stages, input window, output block), one per role and shape:
+    a step allocates nothing, so tensors that cross streams never wait for the caching allocator's cross-stream events
+    (a fresh cudaMalloc per step cost ~6 ms at 8 GPUs).  Stream order makes the reuse safe: a step's side-stream and
+    collective work is joined into the caller's stream before the call returns."""
+    import torch
+    k = (key, tuple(shape), dtype, str(device))
+    t = _halo_buffers.get(k)
+    if t is None:
+        if len(_halo_buffers) > 256:
+            _halo_buffers.clear()
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
+        _halo_buffers[k] = t
+    return t
+
+
+def peer_output_active():
+    """True when some sharded call of this process went through a peer-mapped output image."""
+    return any(v is not None for v in _peer_images.values())
+
+
+def free_exchange_buffers():
+    """Drop the persistent exchange buffers.  With peer-mapped images alive this is a collective over the default
+    group (mappings are closed before the holder frees): call it on every rank at the same point."""
+    _halo_buffers.clear()
+    if any(v is not None for v in _peer_images.values()):
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        for img in _peer_images.values():
+            if img is not None:
+                img.close()
+        if dist.is_initialized():
+            dist.barrier()
+        for img in _peer_images.values():
+            if img is not None:
+                img.free()
+    _peer_images.clear()
 
 
 def _side_stream(dev):
@@ -290,8 +476,8 @@ def _spacing_is_uniform(travel_time_us, dist_km, vel):
 
 
 def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=None, world=None, gather=True,
-                             compute=None, group=None, src=0, pipeline_chunks=4, compute_rows=None, exchange=None,
-                             compute_window=None, window_fn=None):
+                             compute=None, group=None, src=0, pipeline_chunks=DEFAULT_CHUNKS, compute_rows=None, exchange=None,
+                             compute_window=None, window_fn=None, peer_image=None):
     """Kirchhoff migration of one radargram over all ranks of the process group.
 
     x : (snum, tnum) float32 tensor on this rank's device; only rank `src`'s content matters.
@@ -303,8 +489,13 @@ def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=No
     compute(x, travel_time_us, dist_km, vel, nearfield, x_begin, x_end) -> (snum, x_end-x_begin) tensor;
     defaults to the CUDA kernel (tests on CPU/gloo inject their own), likewise compute_rows (row-range entry) and
     compute_window(win, col0, tnum, tt, dist, vel, nearfield, x_begin, x_end, out, rows) (column-window entry).
-    pipeline_chunks > 1: the exchanges and the kernels overlap in bottom-up row chunks (uniform trace spacing; decided
-    on the host identically on every rank - irregular spacing runs the phases back to back)."""
+    pipeline_chunks > 1 (a count, or a sequence of relative chunk heights top to bottom): the exchanges and the
+    kernels overlap in bottom-up row chunks (uniform trace spacing; decided on the host identically on every rank -
+    irregular spacing runs the phases back to back).
+    peer_image (halo exchange with gather='src'): None = automatic - float32 CUDA images computed by the default
+    kernels go through a peer-mapped image (_PeerImage: the other ranks' kernels store their blocks straight into
+    rank src's memory, no output collective) when the mapping works on every rank; False = off (all_to_all gather);
+    or an object with block(xb, xe) / copy_rows_to(out, r0, r1, c0, c1) (tests)."""
     import torch
     import torch.distributed as dist
     default_compute = compute is None
@@ -333,12 +524,17 @@ def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=No
     uniform = _spacing_is_uniform(travel_time_us, dist_km, vel)
     if world > 1 and exchange == 'halo' and compute_window is not None:
         windows = kirchhoff_input_windows(S, T, ranges, travel_time_us, dist_km, vel, window_fn)
-        nchunks = pipeline_chunks if (uniform and pipeline_chunks > 1) else 1
+        many = hasattr(pipeline_chunks, "__len__") or pipeline_chunks > 1
+        nchunks = pipeline_chunks if (uniform and many) else 1
+        peer = peer_image if peer_image not in (None, False) else None
+        if peer_image is None and gather and default_compute and x.is_cuda and x.dtype == torch.float32:
+            peer = _peer_image(S, T, rank, src, world, group, x.device)
         res = _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, world, group, src, ranges,
-                                      windows, nchunks, compute_window, gather)
+                                      windows, nchunks, compute_window, gather, peer)
         return res if gather else (res, (xb, xe))
     broadcast_done = False
-    if world > 1 and gather is True and pipeline_chunks > 1 and compute_rows is not None and uniform:
+    if world > 1 and gather is True and (hasattr(pipeline_chunks, "__len__") or pipeline_chunks > 1) and \
+            compute_rows is not None and uniform:
         out = _kirchhoff_sharded_pipelined(x, travel_time_us, dist_km, vel, nearfield, rank, world, group, src, ranges,
                                            pipeline_chunks, compute_rows)
         if out is not None:
@@ -366,7 +562,7 @@ def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=No
 
 
 def kirchhoff_sharded_host(data, snum, tnum, travel_time_us, dist_km, vel, nearfield, rank=None, world=None, group=None,
-                           src=0, pipeline_chunks=4):
+                           src=0, pipeline_chunks=DEFAULT_CHUNKS):
     """Host-to-host form of the sharded migration (what a torchrun script calls with the radargram loaded on rank
     `src`): `data` is the (snum, tnum) host array on `src` (None elsewhere); returns the float64 migrated image as a
     host array on `src` (page-locked, like RadarData.migrate's result), None elsewhere."""

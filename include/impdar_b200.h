@@ -195,6 +195,19 @@ int impdar_kirchhoff_last_path(void);
 int impdar_kirchhoff_last_tile_standdown(int *stood_down);
 int impdar_kirchhoff_last_stats(unsigned long long *pairs, unsigned long long *exact_pairs);
 
+/* Peer-mapped image (multi-GPU Kirchhoff, the serial trace loop of mig_python.py:35-60 split into output-trace ranges
+ * over one process per GPU): the rank that holds the radargram allocates the (snum, tnum) image with impdar_peer_alloc
+ * (cudaMalloc on the current device; `handle64` HOST, 64 bytes: the CUDA IPC handle to hand to the other processes of
+ * the node), every other rank maps it with impdar_peer_open (current device = its own GPU; peer access over NVLink /
+ * NVSwitch) and passes `mapped + x_begin` with ldo = tnum as `out` of impdar_kirchhoff_window_f32: the diffraction-sum
+ * kernels store their block straight into the holder's memory while they run.  Close every mapping before the holder
+ * frees.  impdar_copy2d_f32 is a strided device-to-device block copy (rows x cols floats) on `stream`.            */
+int impdar_peer_alloc(size_t bytes, void **ptr, void *handle64);
+int impdar_peer_free(void *ptr);
+int impdar_peer_open(const void *handle64, void **ptr);
+int impdar_peer_close(void *ptr);
+int impdar_copy2d_f32(const float *src, size_t lds, float *dst, size_t ldd, int rows, int cols, void *stream);
+
 /* Reference prototype, migrationlib/mig_cython.h:11 - HOST pointers, float64, synchronous.  Linking
  * the reference's own Cython shim (_mig_cython.pyx) against libimpdar_b200.so resolves this symbol.
  * nearfield != 0 needs the un-differentiated data, which this prototype does not carry: the call then

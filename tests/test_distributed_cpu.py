@@ -2,6 +2,7 @@
 the oracle, injected as `compute`, so no GPU is needed)."""
 import os
 import socket
+import tempfile
 
 import numpy as np
 import torch
@@ -17,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, shm_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -100,6 +101,37 @@ def _worker(rank, world, port, q):
     else:
         assert out4 is None
     assert [c[2:4] for c in wcalls] == list(reversed(parallel.row_chunks(S2, 3)))
+    # the peer-mapped output image, stood in for by a file both processes map: rank 1's block is written straight
+    # into "rank 0's memory", rank 0 learns from the per-chunk all_reduce that the rows are there and copies them out
+    class SharedImage(object):
+        def __init__(self, path):
+            self.img = torch.from_file(path, shared=True, size=S2 * T2, dtype=torch.float32).view(S2, T2)
+            self.copies = []
+
+        def block(self, xb, xe):
+            return self.img[:, xb:xe]
+
+        def copy_rows_to(self, out, r0, r1, c0, c1):
+            self.copies.append((r0, r1, c0, c1))
+            out[r0:r1, c0:c1] = self.img[r0:r1, c0:c1]
+
+    shared = SharedImage(shm_path)
+    if rank == 0:
+        shared.img.fill_(float('nan'))
+    dist.barrier()
+    del wcalls[:]
+    out5 = parallel.kirchhoff_sharded_device(x4, tt2, dk2, 1.69e8, False, rank=rank, world=world, gather='src',
+                                             compute=compute, compute_window=compute_window, window_fn=window_fn,
+                                             pipeline_chunks=(1, 2, 1), peer_image=shared)
+    rngs = parallel.kirchhoff_output_ranges(T2, world, tt2, dk2, 1.69e8)
+    if rank == 0:
+        assert np.array_equal(out5.numpy(), out4.numpy())               # same bits as the all_to_all gather
+        assert shared.copies == [(r0, r1, c0, c1) for r0, r1 in reversed(parallel.row_chunks(S2, (1, 2, 1)))
+                                 for c0, c1 in ((0, rngs[0][0]), (rngs[0][1], T2)) if c1 > c0]
+        assert np.isnan(shared.img[:, rngs[0][0]:rngs[0][1]].numpy()).all()    # rank 0 wrote its block into `out` itself
+    else:
+        assert out5 is None and shared.copies == []
+    assert [c[2:4] for c in wcalls] == list(reversed(parallel.row_chunks(S2, (1, 2, 1))))
     blk4, rng4 = parallel.kirchhoff_sharded_device(x4, tt2, dk2, 1.69e8, False, rank=rank, world=world, gather=False,
                                                    compute=compute, compute_window=compute_window, window_fn=window_fn,
                                                    pipeline_chunks=1)
@@ -115,7 +147,10 @@ def test_kirchhoff_sharded_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    shm = tempfile.NamedTemporaryFile(suffix=".img")
+    shm.truncate(40 * 400 * 4)
+    shm.flush()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, shm.name)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]
