@@ -373,9 +373,12 @@ class KirchhoffC5(KirchhoffC2):
         if self.world == 1:
             return "one GPU, whole image"
         if self.parallel.peer_output_active():
-            return ("equal output-trace ranges per GPU; in the timed step: NCCL halo send/recv of the input columns, and the "
-                    "diffraction-sum kernels store their output blocks straight into rank 0's image through peer-mapped "
-                    "memory (CUDA IPC over NVLink), one-element all_reduce per row chunk as completion signal")
+            inp = ("rank 0 pushes every rank's input-column window into that rank's peer-mapped buffer (strided 2-D copies "
+                   "over NVLink, one-element NCCL broadcast per row chunk as the signal)" if self.parallel.peer_input_active()
+                   else "NCCL halo send/recv of the input columns")
+            return ("equal output-trace ranges per GPU; in the timed step: %s, and the diffraction-sum kernels store their "
+                    "output blocks straight into rank 0's image through peer-mapped memory (CUDA IPC over NVLink), "
+                    "one-element NCCL all_reduce per row chunk as completion signal" % inp)
         return "output-trace ranges per GPU; NCCL halo send/recv of the input columns + gather of the output blocks in the timed step"
 
     def setup(self):
@@ -451,6 +454,7 @@ class KirchhoffC5(KirchhoffC2):
     def roofline(self, ms, hbm_gbs, src):
         r = kirchhoff_roofline(self, ms, hbm_gbs, src, self.pairs_rank, self.pairs, self.exact_pairs)
         if self.world > 1:
+            r["kernel_ms_per_step_by_rank"] = getattr(self, "kernel_ms_by_rank", None)
             r["note"] = ("achieved/peak are per GPU (rank 0's kernel and rank 0's share of the pairs; every rank owns the "
                          "same number of output traces - the table kernels' cost is per trace - so the end ranks, whose "
                          "apertures are cut by the profile ends, count fewer pairs for the same work); the step adds the "
@@ -901,6 +905,14 @@ def measure(wl, ctx, steps, warmup, with_e2e=True, with_cpu=False, with_parity=T
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / steps
     value = wl.units * world / (ms_per_step * 1e-3)
+    if world > 1 and wl.scaling == "strong":
+        # every rank's own kernel time per step (load balance of the output-trace ranges), gathered for rank 0's line
+        kt = kernel_times(list(KIRCH_KERNELS))
+        mine = max([v[0] * v[1] for v in kt.values()] + [0.0]) / steps
+        allk = torch.zeros(world, dtype=torch.float64, device="cuda")
+        allk[rank] = mine
+        dist.all_reduce(allk)
+        wl.kernel_ms_by_rank = [round(float(v), 3) for v in allk.tolist()]
     roof = wl.roofline(ms_per_step, ctx.hbm_gbs, ctx.peak_src) if rank == 0 else None
 
     parity = None

@@ -66,7 +66,7 @@ int impdar_copy2d_f32(const float *src, size_t lds, float *dst, size_t ldd, int 
                      "copy2d: bad block %d x %d / strides", rows, cols);
     if (rows == 0 || cols == 0) return IMPDAR_B200_OK;
     IMPDAR_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(float), src, lds * sizeof(float), (size_t)cols * sizeof(float),
-                                  (size_t)rows, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+                                  (size_t)rows, cudaMemcpyDefault, (cudaStream_t)stream));
     return IMPDAR_B200_OK;
 }
 

@@ -66,7 +66,7 @@ def kirchhoff_output_ranges(tnum, world, travel_time_us, dist_km, vel, align=8):
         # whole 256-trace CTA tiles per rank where the ranges are wide enough for that not to unbalance them
         tile = 256 if tnum >= 8 * 256 * world else align
         bounds = [min(int(round(tnum * r / world / tile)) * tile, tnum) for r in range(world)]
-        bounds = [max(b, 0) for b in np.maximum.accumulate(bounds)]
+        bounds = [int(b) for b in np.maximum.accumulate(bounds)]
     else:
         cost = kirchhoff_trace_cost(tt, dk, vel)
         cum = np.concatenate([[0.0], np.cumsum(cost)])
@@ -165,7 +165,7 @@ def kirchhoff_input_windows(snum, tnum, ranges, travel_time_us, dist_km, vel, wi
 
 
 def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, world, group, src, ranges, windows,
-                            nchunks, compute_window, gather, peer=None):
+                            nchunks, compute_window, gather, peer=None, peer_in=None):
     """Halo exchange: rank `src` holds the radargram; every other rank receives ONLY the columns its output range can
     read (its window), bottom-up in row chunks, computes each chunk of its range as soon as the rows are there and
     ships the finished rows to `src` (gather == 'src') while the next chunk runs.  Both exchanges are one
@@ -173,7 +173,9 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
     from its own image into the final one.  With `peer` (a _PeerImage: rank src's persistent image mapped into every
     rank) nothing is shipped at all: the kernels of the other ranks store their blocks into src's memory over NVLink
     as they run, a one-element all_reduce per chunk tells src that the chunk's rows are complete everywhere, and src
-    copies them into the image it returns on its side stream.  Returns the (snum, tnum) image on `src` (None
+    copies them into the image it returns on its side stream.  With `peer_in` (a _PeerWindows: every rank's window
+    buffer mapped into rank src) the input windows are not packed and sent either: src pushes them as strided 2-D
+    copies over NVLink, one stream per destination, and broadcasts one element per chunk as the "landed" signal.  Returns the (snum, tnum) image on `src` (None
     elsewhere) for gather == 'src', or this rank's (snum, range) block for gather False."""
     import torch
     import torch.distributed as dist
@@ -207,7 +209,18 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
         import contextlib
         return torch.cuda.stream(side) if use_side else contextlib.nullcontext()
 
-    win = x[:, c0:c1] if is_src else _halo_buffer("win", (S, c1 - c0), dt, dev)
+    use_peer_in = peer_in is not None and peer is not None and bool(gather)
+    if is_src:
+        win = x[:, c0:c1]
+    elif use_peer_in:
+        win = peer_in.window()                     # this rank's own buffer; rank src writes it through its mapping
+    else:
+        win = _halo_buffer("win", (S, c1 - c0), dt, dev)
+    if use_peer_in and is_src:
+        lanes = _peer_streams(dev, world)
+        for r in range(world):
+            if r != src and windows[r][1] > windows[r][0]:
+                lanes[r].wait_stream(main)
     arrive = {}
     u_hi = S
     for j in reversed(range(len(chunks))):
@@ -216,7 +229,19 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
             arrive[j] = None
             continue
         rows = u_hi - u0
-        if is_src:
+        if use_peer_in:
+            landed = _halo_buffer(("landed", j), (1,), dt, dev, zero=True)
+            if is_src:
+                for r in range(world):
+                    if r != src and windows[r][1] > windows[r][0]:
+                        with torch.cuda.stream(lanes[r]):
+                            peer_in.push(x, u0, u_hi, windows[r][0], windows[r][1], r)
+                        side.wait_stream(lanes[r])
+                with on_side():                    # stream order: the chunk's copies are complete before the signal leaves
+                    arrive[j] = dist.broadcast(landed, src=src, group=group, async_op=True)
+            else:
+                arrive[j] = dist.broadcast(landed, src=src, group=group, async_op=True)
+        elif is_src:
             sizes = [0 if r == src else rows * (windows[r][1] - windows[r][0]) for r in range(world)]
             with on_side():
                 send = _halo_buffer(("send", j), (sum(sizes),), dt, dev)
@@ -352,7 +377,7 @@ class _PeerImage(object):
 
     def block(self, xb, xe):
         """Columns [xb, xe) of the image as the `out` of kirchhoff_window_device (any rank)."""
-        return _RawBlock(self.address + 4 * xb, (self.S, xe - xb), self.T)
+        return _RawBlock(self.address + 4 * int(xb), (self.S, int(xe) - int(xb)), self.T)
 
     def copy_rows_to(self, out, r0, r1, c0, c1):
         """out[r0:r1, c0:c1] = image[r0:r1, c0:c1] on the current stream (rank src)."""
@@ -360,8 +385,9 @@ class _PeerImage(object):
         from . import _lib, device
         if r1 <= r0 or c1 <= c0:
             return
+        r0, r1, c0, c1 = int(r0), int(r1), int(c0), int(c1)
         off = 4 * (r0 * self.T + c0)
-        dst = out.data_ptr() + out.element_size() * (r0 * out.stride(0) + c0)
+        dst = int(out.data_ptr()) + out.element_size() * (r0 * int(out.stride(0)) + c0)
         _lib.check(self.lib.impdar_copy2d_f32(ctypes.c_void_p(self.address + off), self.T, ctypes.c_void_p(dst),
                                               int(out.stride(0)), r1 - r0, c1 - c0, device.current_stream_ptr()))
 
@@ -378,7 +404,104 @@ class _PeerImage(object):
             self.address = 0
 
 
+class _PeerWindows(object):
+    """The input side of the same idea: every rank but `src` owns one persistent (snum, window width) float32 buffer in
+    cudaMalloc memory and rank `src` maps them all.  The radargram's column windows then travel as strided 2-D copies
+    from src's image straight into the owners' buffers (copy engines over NVLink, one stream per destination, no
+    packing pass, no SMs), a one-element broadcast per row chunk telling the owners that the chunk has landed.
+    Building one is a collective over `group`; `ok` is the same on every rank."""
+
+    def __init__(self, S, widths, rank, src, world, group, dev):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        lib = _lib.load()
+        self.S, self.widths, self.rank, self.src, self.is_src, self.lib = S, [int(w) for w in widths], rank, src, rank == src, lib
+        self.address = 0                  # this rank's own buffer (not on src)
+        self.mapped = {}                  # on src: rank -> address of that rank's buffer in this process
+        good = 1
+        handle = torch.zeros(64, dtype=torch.uint8, device=dev)
+        if not self.is_src and self.widths[rank] > 0:
+            h = (ctypes.c_ubyte * 64)()
+            p = ctypes.c_void_p(0)
+            if lib.impdar_peer_alloc(ctypes.c_size_t(S * self.widths[rank] * 4), ctypes.byref(p), h) == 0:
+                self.address = int(p.value)
+                handle.copy_(torch.frombuffer(bytearray(h), dtype=torch.uint8))
+            else:
+                good = 0
+        handles = torch.zeros((world, 64), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(handles, handle, group=group)
+        if self.is_src:
+            hh = handles.cpu().numpy()
+            for r in range(world):
+                if r == src or self.widths[r] <= 0 or not hh[r].any():
+                    good = good if (r == src or self.widths[r] <= 0) else 0
+                    continue
+                h = (ctypes.c_ubyte * 64).from_buffer_copy(hh[r].tobytes())
+                p = ctypes.c_void_p(0)
+                if lib.impdar_peer_open(h, ctypes.byref(p)) == 0:
+                    self.mapped[r] = int(p.value)
+                else:
+                    good = 0
+        flag = torch.tensor([good], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.ok = bool(int(flag.item()))
+
+    def window(self):
+        """This rank's window buffer as the `win` of kirchhoff_window_device."""
+        w = self.widths[self.rank]
+        return _RawBlock(self.address, (self.S, w), w)
+
+    def push(self, x, u0, u1, c0, c1, r):
+        """Rows [u0, u1) of columns [c0, c1) of src's image `x` into rank r's window buffer, on the current stream."""
+        import ctypes
+        from . import _lib, device
+        u0, u1, c0, c1 = int(u0), int(u1), int(c0), int(c1)
+        w = self.widths[r]
+        assert c1 - c0 == w and x.stride(1) == 1 and x.element_size() == 4
+        src_addr = int(x.data_ptr()) + 4 * (u0 * int(x.stride(0)) + c0)
+        _lib.check(self.lib.impdar_copy2d_f32(ctypes.c_void_p(src_addr), int(x.stride(0)),
+                                              ctypes.c_void_p(self.mapped[r] + 4 * u0 * w), w, u1 - u0, w,
+                                              device.current_stream_ptr()))
+
+    def close(self):
+        import ctypes
+        for a in self.mapped.values():
+            self.lib.impdar_peer_close(ctypes.c_void_p(a))
+        self.mapped = {}
+
+    def free(self):
+        import ctypes
+        if self.address:
+            self.lib.impdar_peer_free(ctypes.c_void_p(self.address))
+            self.address = 0
+
+
 _peer_images = {}
+
+
+def _peer_windows(S, T, windows, rank, src, world, group, dev):
+    """The cached peer-mapped window buffers for this shape and window layout (None: unavailable / switched off with
+    IMPDAR_PEER_INPUT=0; the windows then travel by all_to_all).  Same decision on every rank."""
+    import os
+    widths = tuple(int(b - a) for a, b in windows)
+    key = ("win", S, T, widths, src, world, id(group) if group is not None else None, str(dev))
+    if key not in _peer_images:
+        pw = None
+        if os.environ.get("IMPDAR_PEER_INPUT", "1") != "0":
+            try:
+                pw = _PeerWindows(S, widths, rank, src, world, group, dev)
+            except (RuntimeError, OSError, AttributeError) as e:
+                import warnings
+                warnings.warn("impdar_b200: peer-mapped window buffers unavailable (%s); using all_to_all" % e)
+                pw = None
+            if pw is not None and not pw.ok:
+                pw.close()
+                pw.free()
+                pw = None
+        _peer_images[key] = pw
+    return _peer_images[key]
 
 
 def _peer_image(S, T, rank, src, world, group, dev):
@@ -407,6 +530,17 @@ def _peer_image(S, T, rank, src, world, group, dev):
 
 _side_streams = {}
 _halo_buffers = {}
+_lane_streams = {}
+
+
+def _peer_streams(dev, world):
+    """One copy stream per destination rank (rank src's pushes to different ranks run on different copy engines)."""
+    import torch
+    key = (torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device(), world)
+    if key not in _lane_streams:
+        _lane_streams[key] = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    return _lane_streams[key]
+
 
 
 def _halo_buffer(key, shape, dtype, device, zero=False):
@@ -427,7 +561,12 @@ def _halo_buffer(key, shape, dtype, device, zero=False):
 
 def peer_output_active():
     """True when some sharded call of this process went through a peer-mapped output image."""
-    return any(v is not None for v in _peer_images.values())
+    return any(isinstance(v, _PeerImage) for v in _peer_images.values())
+
+
+def peer_input_active():
+    """True when some sharded call of this process pushed its input windows through peer-mapped buffers."""
+    return any(isinstance(v, _PeerWindows) for v in _peer_images.values())
 
 
 def free_exchange_buffers():
@@ -529,8 +668,13 @@ def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=No
         peer = peer_image if peer_image not in (None, False) else None
         if peer_image is None and gather and default_compute and x.is_cuda and x.dtype == torch.float32:
             peer = _peer_image(S, T, rank, src, world, group, x.device)
+        peer_in = None
+        if peer is not None and peer_image is None:
+            peer_in = _peer_windows(S, T, windows, rank, src, world, group, x.device)
+            if peer_in is not None and rank == src and x.stride(1) != 1:
+                x = x.contiguous()
         res = _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, world, group, src, ranges,
-                                      windows, nchunks, compute_window, gather, peer)
+                                      windows, nchunks, compute_window, gather, peer, peer_in)
         return res if gather else (res, (xb, xe))
     broadcast_done = False
     if world > 1 and gather is True and (hasattr(pipeline_chunks, "__len__") or pipeline_chunks > 1) and \
