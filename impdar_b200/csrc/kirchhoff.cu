@@ -420,10 +420,38 @@ __global__ void __launch_bounds__(128) kirch_table_build_kernel(int2 *__restrict
 __global__ void __launch_bounds__(256) grad_padded_kernel(const float *__restrict__ data, float *__restrict__ gP,
                                                           float *__restrict__ dP, int S, int c0, int ncols, int ld,
                                                           int Tp, int aoff, const double *__restrict__ coef,
-                                                          int *__restrict__ flags, int s0) {
+                                                          int *__restrict__ flags, int s0, int vec4) {
     const int s = s0 + blockIdx.y;
     const double a = coef[s], b = coef[S + s], c = coef[2 * S + s];
     bool bad = false;
+    if (vec4) {
+        // four columns per thread through 128-bit accesses (same arithmetic per element); the host checks alignment
+        const float4 *__restrict__ r0 = reinterpret_cast<const float4 *>(data + (size_t)s * ld);
+        const float4 *__restrict__ rm = reinterpret_cast<const float4 *>(data + (size_t)(s > 0 ? s - 1 : s) * ld);
+        const float4 *__restrict__ rp = reinterpret_cast<const float4 *>(data + (size_t)(s < S - 1 ? s + 1 : s) * ld);
+        float4 *__restrict__ go = reinterpret_cast<float4 *>(gP + (size_t)s * Tp + aoff + c0);
+        float4 *__restrict__ dout = dP ? reinterpret_cast<float4 *>(dP + (size_t)s * Tp + aoff + c0) : nullptr;
+        const bool um = s > 0 && a != 0.0, u0 = b != 0.0, up = s < S - 1 && c != 0.0;
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ncols / 4; j += gridDim.x * blockDim.x) {
+            const float4 d0 = r0[j];
+            const float4 dm = um ? rm[j] : d0, dq = up ? rp[j] : d0;
+            const float v0[4] = {d0.x, d0.y, d0.z, d0.w}, vm[4] = {dm.x, dm.y, dm.z, dm.w}, vp[4] = {dq.x, dq.y, dq.z, dq.w};
+            float g[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double acc = 0.0;
+                if (um) acc += a * (double)vm[i];
+                if (u0) acc += b * (double)v0[i];
+                if (up) acc += c * (double)vp[i];
+                g[i] = (float)acc;
+                if (!isfinite(g[i]) || !isfinite(v0[i])) bad = true;
+            }
+            go[j] = make_float4(g[0], g[1], g[2], g[3]);
+            if (dout) dout[j] = d0;
+        }
+        if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, 1);
+        return;
+    }
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ncols; j += gridDim.x * blockDim.x) {
         const float dv = data[(size_t)s * ld + j];
         double acc = 0.0;
@@ -504,28 +532,36 @@ __device__ __forceinline__ void kirch_table_loop(const KirchTabParams &p, int ti
 template <bool NEAR, bool STATS>
 __global__ void __launch_bounds__(128) kirch_table_kernel(const __grid_constant__ KirchTabParams p) {
     if (p.only_if && !(p.only_if[0] | p.flags[0])) return;   // the tile kernel has done these rows
-    const int ti = p.s_begin + blockIdx.x;
+    // Work item = (row, block of 4 x 32 KT_R output traces), rows fastest.  The grid holds every item when this kernel
+    // is the one that does the work; as the tile kernel's stand-in it is a small grid that strides over the items
+    // (half a million CTAs that only test the flag and leave cost 0.5 ms at 65536 x 8192).
+    const int nrows = p.s_end - p.s_begin;
+    const int ntx = (p.x_end - p.x_begin + 4 * 32 * KT_R - 1) / (4 * 32 * KT_R);
+    const long long nitems = (long long)nrows * ntx;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int xbase = p.x_begin + (blockIdx.y * 4 + warp) * (32 * KT_R) + lane;
-    if (xbase - lane >= p.x_end) return;
-    float acc[KT_R];
+    for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const int ti = p.s_begin + (int)(it % nrows);
+        const int xbase = p.x_begin + ((int)(it / nrows) * 4 + warp) * (32 * KT_R) + lane;
+        if (xbase - lane >= p.x_end) continue;
+        float acc[KT_R];
 #pragma unroll
-    for (int r = 0; r < KT_R; ++r) acc[r] = 0.f;
-    unsigned npairs = 0;
-    if (p.flags[0] != 0)
-        kirch_table_loop<NEAR, true, STATS>(p, ti, xbase, acc, npairs);
-    else
-        kirch_table_loop<NEAR, false, STATS>(p, ti, xbase, acc, npairs);
+        for (int r = 0; r < KT_R; ++r) acc[r] = 0.f;
+        unsigned npairs = 0;
+        if (p.flags[0] != 0)
+            kirch_table_loop<NEAR, true, STATS>(p, ti, xbase, acc, npairs);
+        else
+            kirch_table_loop<NEAR, false, STATS>(p, ti, xbase, acc, npairs);
 #pragma unroll
-    for (int r = 0; r < KT_R; ++r) {
-        const int x = xbase + 32 * r;
-        if (x < p.x_end) p.out[(size_t)ti * p.ldo + (x - p.x_begin)] = acc[r];
-    }
-    if (STATS) {
-        unsigned long long np64 = npairs;
+        for (int r = 0; r < KT_R; ++r) {
+            const int x = xbase + 32 * r;
+            if (x < p.x_end) p.out[(size_t)ti * p.ldo + (x - p.x_begin)] = acc[r];
+        }
+        if (STATS) {
+            unsigned long long np64 = npairs;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) np64 += __shfl_xor_sync(0xffffffffu, np64, o);
-        if (lane == 0 && np64) atomicAdd(&p.stats[0], np64);
+            for (int o = 16; o > 0; o >>= 1) np64 += __shfl_xor_sync(0xffffffffu, np64, o);
+            if (lane == 0 && np64) atomicAdd(&p.stats[0], np64);
+        }
     }
 }
 
@@ -542,8 +578,11 @@ __global__ void __launch_bounds__(256) kirch_table_fixup_kernel(const __grid_con
     const int wid = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
     // Entries outside this launch's row range are skipped with one load each (row-chunked launches would otherwise
-    // walk the whole (entry, block) space every time); an in-range entry is spread over `split` warps.
-    const int split = 8;
+    // walk the whole (entry, block) space every time); an in-range entry is spread over `split` warps (8 when the
+    // list is long, up to one warp per block when it is short: one entry x 2048 blocks on 8 warps took 0.42 ms).
+    int split = nwarps / (count > 0 ? count : 1);   // a handful of entries (the usual case): all warps share their blocks
+    split = split < 8 ? 8 : (split > nblk ? nblk : split);
+    if (split < 1) split = 1;
     for (long long it = wid; it < (long long)count * split; it += nwarps) {
         const int e = amb_list[it / split];
         const int ti = e / tp.A1, m = e % tp.A1;
@@ -687,8 +726,10 @@ int impdar_kirchhoff_input_window(int S, int T, const double *dist_m, const doub
     }
     lo -= 2;
     hi += 2;
-    *col0 = lo < 0 ? 0 : lo;
-    *col1 = hi + 1 > T ? T : hi + 1;
+    lo = lo < 0 ? 0 : lo & ~3;                      // whole groups of four columns: the window's rows stay 16-byte
+    int end = (hi + 1 + 3) & ~3;                    // aligned in the image and in a packed copy (128-bit d/dt pass)
+    *col0 = lo;
+    *col1 = end > T ? T : end;
     return IMPDAR_B200_OK;
 }
 
@@ -880,10 +921,13 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
             {
                 const int g0 = r0;   // row r0 - 1 is uploaded (or r0 == 0: one-sided stencil)
                 if (g0 < g_hi) {
-                    int gx = (ncols + 255) / 256;
+                    // 128-bit path: data rows and the padded rows 16-byte aligned (aoff + c0 = Apad is a multiple of 32)
+                    const int vec4 = (((uintptr_t)data & 15) == 0 && ld % 4 == 0 && ncols % 4 == 0) ? 1 : 0;
+                    const int per_row = vec4 ? ncols / 4 : ncols;
+                    int gx = (per_row + 255) / 256;
                     if (gx > 64) gx = 64;
                     dim3 grid(gx, g_hi - g0);
-                    grad_padded_kernel<<<grid, 256, 0, st>>>(data, gP, dP, S, c0, ncols, ld, Tp, aoff, d_coef, flags, g0);
+                    grad_padded_kernel<<<grid, 256, 0, st>>>(data, gP, dP, S, c0, ncols, ld, Tp, aoff, d_coef, flags, g0, vec4);
                     IMPDAR_LAUNCH_CHECK();
                     g_hi = g0;
                 }
@@ -908,7 +952,10 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
                 ktimer_end(st);
                 IMPDAR_LAUNCH_CHECK();
             }
-            dim3 grid(r1 - r0, (x_end - x_begin + 4 * 32 * KT_R - 1) / (4 * 32 * KT_R));
+            const long long nitems = (long long)(r1 - r0) * ((x_end - x_begin + 4 * 32 * KT_R - 1) / (4 * 32 * KT_R));
+            IMPDAR_CHECK_ARG(nitems < (1ll << 31), "kirchhoff: launch too large");
+            // stand-in for the tile kernel: a grid that fills the GPU once and strides; otherwise one CTA per item
+            const unsigned grid = (unsigned)(use_tile && nitems > (long long)num_sms() * 16 ? num_sms() * 16 : nitems);
             ktimer_begin("kirch_table_kernel", st);
             if (nearfield) kirch_table_kernel<true, false><<<grid, 128, 0, st>>>(tp);
             else kirch_table_kernel<false, false><<<grid, 128, 0, st>>>(tp);

@@ -134,6 +134,33 @@ def test_kirchhoff_sharded_equals_unsharded():
     assert torch.equal(one, parts[3])
 
 
+@pytest.mark.parametrize("T", [6000, 6002])
+def test_kirchhoff_column_window_equals_unsharded(T):
+    """The unit of the multi-GPU exchange: a rank holds only the input columns its output range can read - as a packed
+    copy (what a peer-mapped window buffer is) or as a strided slice of the image (what the holding rank uses) - and
+    writes its block through a row stride (its place in the final image).  Bit for bit the unsharded image, for row
+    chunks of unequal height, with and without the 128-bit d/dt pass (T = 6002: image rows are not 16-byte aligned)."""
+    import torch
+    from impdar_b200 import migrationlib as ml, parallel
+    S = 1024
+    x = _noise(S, T, 29)
+    tt, dist = _geometry(S, T)
+    whole = ml.kirchhoff_device(x, tt, dist, VEL, False)
+    xd = x
+    ranges = parallel.kirchhoff_output_ranges(T, 4, tt, dist, VEL)
+    assert ranges[0][0] == 0 and ranges[-1][1] == T
+    image = torch.full((S, T), float('nan'), dtype=torch.float32, device="cuda")
+    for i, (xb, xe) in enumerate(ranges):
+        c0, c1 = ml.kirchhoff_input_window(S, tt, dist, VEL, xb, xe)
+        assert c0 % 4 == 0 and (c1 % 4 == 0 or c1 == T) and c0 <= xb and c1 >= xe and c1 - c0 < T
+        win = xd[:, c0:c1].contiguous() if i % 2 == 0 else xd[:, c0:c1]
+        g_hi = S
+        for r0, r1 in reversed(parallel.row_chunks(S, parallel.DEFAULT_CHUNKS)):
+            ml.kirchhoff_window_device(win, c0, T, tt, dist, VEL, False, xb, xe, image[:, xb:xe], (r0, r1, g_hi))
+            g_hi = r0
+    assert torch.equal(image, whole)
+
+
 @pytest.mark.parametrize("layered", [False, True])
 def test_phase_shift_4096_samples(layered):
     """S = nt = 4096 (config 3's depth: phases up to ~1e4 rad, 64 re-seeded recurrence blocks) on a trace crop the
