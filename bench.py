@@ -49,7 +49,7 @@ def load_peaks():
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler(object):
-    """SM clock / throttle-reason sampling DURING the timed region (NVML, 5 ms period; the nvidia-smi
+    """SM clock / throttle-reason sampling DURING the timed region (NVML, 1 ms period for the first 16 samples, then 20 ms; the nvidia-smi
     query line of B200_PROFILING.md reads the same counters)."""
 
     def __init__(self, gpu_index):
@@ -86,9 +86,11 @@ class ClockSampler(object):
                     for n, bit in names.items():
                         if r & bit:
                             self.reasons.add(n)
-                    time.sleep(0.001)
+                    # dense at first (the short workloads last a few ms), then 50 Hz: a thread that wakes every
+                    # millisecond competes with the enqueueing thread for the interpreter lock
+                    time.sleep(0.001 if len(self.sm) < 16 else 0.02)
                 else:
-                    time.sleep(0.0005)
+                    time.sleep(0.002)
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
 

@@ -662,6 +662,50 @@ static int kirch_pipe_streams(KirchPipe **out) {
     return IMPDAR_B200_OK;
 }
 
+// Geometry vectors (travel times, d/dt coefficients, trace positions) go up through a small ring of page-locked staging
+// buffers per device: an asynchronous copy from pageable memory makes the HOST wait until the stream has drained, which
+// kept the caller from enqueueing the next call (or the next step of a multi-GPU pipeline) while this one runs.
+constexpr int KV_SLOTS = 4;
+struct KirchVecSlot {
+    void *host;
+    size_t cap;
+    cudaEvent_t ev;
+    bool used;
+};
+struct KirchVecRing {
+    KirchVecSlot slot[KV_SLOTS];
+    int next;
+};
+static KirchVecRing g_vecs[KP_MAX_DEVICES];
+static int kirch_stage_vectors(const double *tt, const double *coef, const double *dist, int S, int T, double *d_dst,
+                               cudaStream_t st) {
+    int dev = 0;
+    IMPDAR_CUDA(cudaGetDevice(&dev));
+    IMPDAR_CHECK_ARG(dev >= 0 && dev < KP_MAX_DEVICES, "kirchhoff: device index %d out of range", dev);
+    const size_t bytes = ((size_t)4 * S + (size_t)T) * sizeof(double);
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    KirchVecRing &ring = g_vecs[dev];
+    KirchVecSlot &sl = ring.slot[ring.next];
+    ring.next = (ring.next + 1) % KV_SLOTS;
+    if (sl.used) IMPDAR_CUDA(cudaEventSynchronize(sl.ev));   // the copy that last read this slot has run
+    if (!sl.ev) IMPDAR_CUDA(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    if (sl.cap < bytes) {
+        if (sl.host) IMPDAR_CUDA(cudaFreeHost(sl.host));
+        sl.host = nullptr;
+        sl.cap = 0;
+        IMPDAR_CUDA(cudaHostAlloc(&sl.host, bytes, cudaHostAllocDefault));
+        sl.cap = bytes;
+    }
+    double *h = (double *)sl.host;
+    memcpy(h, tt, (size_t)S * sizeof(double));
+    memcpy(h + S, coef, (size_t)3 * S * sizeof(double));
+    memcpy(h + (size_t)4 * S, dist, (size_t)T * sizeof(double));
+    IMPDAR_CUDA(cudaMemcpyAsync(d_dst, h, bytes, cudaMemcpyHostToDevice, st));
+    IMPDAR_CUDA(cudaEventRecord(sl.ev, st));
+    sl.used = true;
+    return IMPDAR_B200_OK;
+}
+
 static thread_local unsigned long long *g_last_stats = nullptr;
 static thread_local const int *g_last_flags = nullptr;
 static thread_local cudaStream_t g_last_stats_stream = nullptr;
@@ -816,13 +860,15 @@ static int kirchhoff_impl(const float *data, float *out, int S, int T, const dou
     unsigned long long *stats = (unsigned long long *)(w + 128);
     w += 256;
     w = (char *)(((uintptr_t)w + 255) & ~(uintptr_t)255);
-    IMPDAR_CUDA(cudaMemcpyAsync(d_tt, tt_s, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
-    IMPDAR_CUDA(cudaMemcpyAsync(d_coef, grad_coef, 3 * (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
-    IMPDAR_CUDA(cudaMemcpyAsync(d_dist, dist_m, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, st));
-    const bool continuing = rows && rows->g_hi < S;   // later call of a bottom-up row sequence: flags, tables, d/dt rows stay
-    if (!continuing) IMPDAR_CUDA(cudaMemsetAsync(flags, 0, 256, st));
-    kirch_prep_vectors_kernel<<<(S + 255) / 256, 256, 0, st>>>(d_tt, zs, zs2, S, vel);
-    IMPDAR_LAUNCH_CHECK();
+    const bool continuing = rows && rows->g_hi < S;   // later call of a bottom-up row sequence: flags, tables, d/dt rows
+    if (!continuing) {                                // and the vectors stay (same workspace, same stream)
+        // d_tt | d_coef (3 S) | d_dist are contiguous in the workspace: one copy from the page-locked staging slot
+        int rcv = kirch_stage_vectors(tt_s, grad_coef, dist_m, S, T, d_tt, st);
+        if (rcv) return rcv;
+        IMPDAR_CUDA(cudaMemsetAsync(flags, 0, 256, st));
+        kirch_prep_vectors_kernel<<<(S + 255) / 256, 256, 0, st>>>(d_tt, zs, zs2, S, vel);
+        IMPDAR_LAUNCH_CHECK();
+    }
 
     KirchParams p;
     memset(&p, 0, sizeof(p));

@@ -189,10 +189,10 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
     import os
     trace = [] if (os.environ.get("IMPDAR_TRACE_SHARDED") and x.is_cuda) else None
 
-    def mark(label):
+    def mark(label, stream=None):
         if trace is not None:
             ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
+            ev.record(stream) if stream is not None else ev.record()
             trace.append((label, ev))
 
     mark("start")
@@ -200,6 +200,7 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
     # packing of the other ranks' column slabs and, later, the filing of their finished rows run on a side stream: the
     # compute stream of `src` only ever waits for the kernels of its own range.
     use_side = x.is_cuda
+    side = None
     if use_side:
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev)
@@ -237,6 +238,7 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
                         with torch.cuda.stream(lanes[r]):
                             peer_in.push(x, u0, u_hi, windows[r][0], windows[r][1], r)
                         side.wait_stream(lanes[r])
+                mark("window %d pushed" % j, side)
                 with on_side():                    # stream order: the chunk's copies are complete before the signal leaves
                     arrive[j] = dist.broadcast(landed, src=src, group=group, async_op=True)
             else:
@@ -302,6 +304,7 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
                 for a, b in ((0, xb), (xe, T)):    # the other ranks' columns, either side of this rank's own
                     if b > a:
                         peer.copy_rows_to(out, r0, r1, a, b)
+                mark("chunk %d filed" % j, side)
             elif is_src:
                 r0, r1 = chunks[j]
                 off = 0

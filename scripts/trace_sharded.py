@@ -16,7 +16,7 @@ for _ in range(3):
     parallel.kirchhoff_sharded_device(x, tt, dk, 1.69e8, False, rank=rank, world=world, gather='src')
 torch.cuda.synchronize(); dist.barrier()
 os.environ["IMPDAR_TRACE_SHARDED"] = "1"
-for chunks in (4, 1):
+for chunks in (parallel.DEFAULT_CHUNKS, 4, 1):
     if rank == 0:
         print("pipeline_chunks =", chunks, flush=True)
     for _ in range(2):
