@@ -169,3 +169,57 @@ def test_install_rebinds_reference_seam():
     finally:
         impdar_b200.uninstall()
     assert ref_mig.migrationStolt is orig
+
+
+def test_peer_image_and_window_address_arithmetic(monkeypatch):
+    """The peer-mapped image / window helpers (impdar_b200/parallel.py) hand raw addresses to impdar_copy2d_f32 and to
+    the column-window entry: byte offsets, row strides and plain-int conversion (range bounds arrive as numpy integers)
+    checked against a recording stand-in of the C library - no GPU involved."""
+    import ctypes
+    import numpy as np
+    import torch
+    from impdar_b200 import parallel, device, _lib
+
+    calls = []
+
+    class Lib(object):
+        def impdar_copy2d_f32(self, src, lds, dst, ldd, rows, cols, stream):
+            for v in (lds, ldd, rows, cols):
+                assert type(v) is int
+            calls.append((src.value, lds, dst.value, ldd, rows, cols))
+            return 0
+
+    monkeypatch.setattr(device, "current_stream_ptr", lambda: ctypes.c_void_p(0))
+    monkeypatch.setattr(_lib, "check", lambda rc, *a: None)
+    S, T = 16, 40
+    img = object.__new__(parallel._PeerImage)
+    img.S, img.T, img.src, img.is_src, img.lib, img.address = S, T, 0, True, Lib(), 1 << 20
+    out = torch.zeros((S, T), dtype=torch.float32)
+    img.copy_rows_to(out, np.int64(2), np.int64(5), np.int64(8), np.int64(24))
+    assert calls[-1] == ((1 << 20) + 4 * (2 * T + 8), T, out.data_ptr() + 4 * (2 * T + 8), T, 3, 16)
+    view = out[:, 4:]                                        # a column slice of the final image keeps the row stride
+    img.copy_rows_to(view, 0, S, 0, 4)
+    assert calls[-1] == (1 << 20, T, view.data_ptr(), T, S, 4)
+    n = len(calls)
+    img.copy_rows_to(out, 3, 3, 0, 4)                        # empty blocks are not issued
+    img.copy_rows_to(out, 0, 4, 7, 7)
+    assert len(calls) == n
+    blk = img.block(np.int64(8), np.int64(24))
+    assert blk.data_ptr() == (1 << 20) + 32 and blk.shape == (S, 16) and blk.stride(0) == T and blk.stride(1) == 1
+    assert device.ptr(blk).value == blk.data_ptr()
+
+    win = object.__new__(parallel._PeerWindows)
+    win.S, win.widths, win.rank, win.src, win.is_src, win.lib = S, [0, 12, 20], 0, 0, True, Lib()
+    win.address, win.mapped = 0, {1: 1 << 24, 2: 1 << 25}
+    x = torch.zeros((S, T), dtype=torch.float32)
+    win.push(x, np.int64(3), np.int64(9), np.int64(4), np.int64(16), 1)
+    assert calls[-1] == (x.data_ptr() + 4 * (3 * T + 4), T, (1 << 24) + 4 * 3 * 12, 12, 6, 12)
+    try:
+        win.push(x, 0, 4, 0, 16, 1)                          # not rank 1's window width
+    except AssertionError:
+        pass
+    else:
+        raise AssertionError("push must check the window width")
+    win.rank, win.is_src, win.address = 2, False, 1 << 26
+    w = win.window()
+    assert w.data_ptr() == 1 << 26 and w.shape == (S, 20) and w.stride(0) == 20
