@@ -238,12 +238,6 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
                         with torch.cuda.stream(lanes[r]):
                             peer_in.push(x, u0, u_hi, windows[r][0], windows[r][1], r)
                         side.wait_stream(lanes[r])
-                # chunk j - 1 leaves on every lane only when chunk j has landed everywhere: the copy engines drain the
-                # lanes unevenly otherwise (profiles/r02s_trace_sharded_n4.txt: the second chunk complete on all ranks
-                # only when 3/4 of ALL the data had moved) and every rank waits for the chunk it needs next
-                for r in range(world):
-                    if r != src and windows[r][1] > windows[r][0]:
-                        lanes[r].wait_stream(side)
                 mark("window %d pushed" % j, side)
                 with on_side():                    # stream order: the chunk's copies are complete before the signal leaves
                     arrive[j] = dist.broadcast(landed, src=src, group=group, async_op=True)
