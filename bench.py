@@ -178,6 +178,18 @@ class Workload(object):
     parallelism = "independent radargrams per GPU, no collective"
     steps_timed = 1
 
+    def parallelism_for(self, world):
+        return self.parallelism
+
+    def config(self, world=None):
+        """The `config` object of the JSON line - the same for this arm and for `--impl reference` at the same --gpus."""
+        world = self.world if world is None else world
+        return {"workload": self.name, "snum": self.S, "tnum": getattr(self, "T_full", self.T), "l2": self.l2_note(),
+                "parallelism": "1 process per GPU, %s" % self.parallelism_for(world)}
+
+    def exchange_note(self):
+        return None
+
     def parity(self):
         return None
 
@@ -370,18 +382,24 @@ class KirchhoffC5(KirchhoffC2):
                "impdar_b200.parallel.kirchhoff_sharded_host - rank 0 uploads, halo exchange, kernels, gather to rank 0, "
                "float64 download")
 
-    @property
-    def parallelism(self):
-        if self.world == 1:
+    def parallelism_for(self, world):
+        if world == 1:
             return "one GPU, whole image"
+        return ("one radargram, equal output-trace ranges per GPU; halo exchange of the input columns and gather of the "
+                "output blocks on rank 0 inside the timed step")
+
+    def exchange_note(self):
+        """How the exchange of the timed steps actually travelled (decided at run time: peer mappings can be refused)."""
+        if self.world == 1:
+            return None
         if self.parallel.peer_output_active():
             inp = ("rank 0 pushes every rank's input-column window into that rank's peer-mapped buffer (strided 2-D copies "
                    "over NVLink, one-element NCCL broadcast per row chunk as the signal)" if self.parallel.peer_input_active()
-                   else "NCCL halo send/recv of the input columns")
-            return ("equal output-trace ranges per GPU; in the timed step: %s, and the diffraction-sum kernels store their "
-                    "output blocks straight into rank 0's image through peer-mapped memory (CUDA IPC over NVLink), "
-                    "one-element NCCL all_reduce per row chunk as completion signal" % inp)
-        return "output-trace ranges per GPU; NCCL halo send/recv of the input columns + gather of the output blocks in the timed step"
+                   else "NCCL all_to_all send/recv of the input columns")
+            return ("%s; the diffraction-sum kernels store their output blocks straight into rank 0's image through "
+                    "peer-mapped memory (CUDA IPC over NVLink), one-element NCCL all_reduce per row chunk as completion "
+                    "signal" % inp)
+        return "NCCL all_to_all send/recv of the input columns and of the output blocks, one per row chunk"
 
     def setup(self):
         import torch
@@ -595,7 +613,7 @@ class PipelineC4(Workload):
         self.e2e_units = self.P * self.S * self.T
 
     def l2_note(self):
-        return "inputs larger than L2" if self.P * self.S * self.T * 4 > 126e6 else Workload.l2_note(self)
+        return "inputs larger than L2" if self.args.profiles * self.S * self.T * 4 > 126e6 else Workload.l2_note(self)
 
     def step(self):
         from impdar_b200 import filtering as fl, migrationlib as ml
@@ -847,7 +865,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "migrated samples/s", "value": value, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3,
             "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl.name, "snum": wl.S, "tnum": getattr(wl, "T_full", wl.T)},
+            "config": wl.config(world=args.gpus),          # this arm runs on the other arm's config
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample,
                              "host_cores_available": os.cpu_count()},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -944,8 +962,7 @@ def measure(wl, ctx, steps, warmup, with_e2e=True, with_cpu=False, with_parity=T
     if rank == 0:
         rec = {"value": value, "unit": "samples/s", "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
                "scaling": wl.scaling, "dtype": wl.dtype,
-               "config": {"workload": wl.name, "snum": wl.S, "tnum": wl.T, "l2": wl.l2_note(),
-                          "parallelism": "1 process per GPU, %s" % wl.parallelism},
+               "config": wl.config(), "exchange": wl.exchange_note(),
                "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "parity": parity}
         if with_cpu:
             n = ctx.args.cpu_samples or wl.cpu_default_n
@@ -1016,7 +1033,8 @@ def main():
         line = {"metric": "migrated samples/s", "value": head["value"], "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
                 "scaling": head["scaling"], "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
-                "config": head["config"], "clocks": head["clocks"], "gpu_launches": head["gpu_launches"],
+                "config": head["config"], "exchange": head["exchange"], "clocks": head["clocks"],
+                "gpu_launches": head["gpu_launches"],
                 "e2e": head["e2e"], "roofline": head["roofline"], "parity": head["parity"], "peak_source": ctx.peak_src}
         if "cpu_baseline" in head:
             line["cpu_baseline"] = head["cpu_baseline"]

@@ -223,3 +223,24 @@ def test_peer_image_and_window_address_arithmetic(monkeypatch):
     win.rank, win.is_src, win.address = 2, False, 1 << 26
     w = win.window()
     assert w.data_ptr() == 1 << 26 and w.shape == (S, 20) and w.stride(0) == 20
+
+
+def test_bench_config_is_the_same_object_for_both_arms():
+    """`bench.py --impl reference` must print the `config` of our arm's line at the same --gpus (the driver compares
+    them): both come from Workload.config(), which depends on the workload and the GPU count only."""
+    import argparse
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    args = argparse.Namespace(gpus=1, steps=1, warmup=0, profiles=8, workload='kirchhoff_c5', cpu_samples=0)
+    for name, cls in bench.WORKLOADS.items():
+        for world in (1, 2, 8):
+            ours = cls(args, 0, world).config()                 # what measure() prints on rank 0 of `world` ranks
+            ref = cls(args, 0, 1).config(world=world)           # what run_reference() prints with --gpus world
+            assert ours == ref and set(ours) == {"workload", "snum", "tnum", "l2", "parallelism"}, (name, world)
+    c5 = bench.WORKLOADS["kirchhoff_c5"]
+    assert c5(args, 0, 1).config()["parallelism"] != c5(args, 0, 8).config()["parallelism"]
+    assert "65536" in c5.name and (c5.S, c5.T) == (8192, 65536)
