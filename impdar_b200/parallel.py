@@ -14,6 +14,15 @@ import numpy as np
 # (nothing can start before it) and the top chunk's rows are the last to reach the image: both small; measured at 8 GPUs
 # on 65536 x 8192 (profiles/r02m_exchange_variants_n8.txt): 4 equal chunks 36.3 ms, (1, 2, 2, 2, 1) 29.7, this 29.4.
 DEFAULT_CHUNKS = (1, 2, 3, 3, 2, 1)
+# Below this many samples the chunked pipeline loses to one chunk (every chunk costs its own table-schedule, d/dt and tile
+# launches with their tails): 4096 x 16384 = 6.7e7 samples took 3.3 / 4.0 / 6.7 ms in one chunk against 4.4 / 5.2 / 7.8 ms in six
+# on 8 / 4 / 2 GPUs (profiles/r02[opr]_check_sharded_n*.txt); 65536 x 8192 = 5.4e8 samples gains 7 ms from it at 8 GPUs.
+CHUNKING_MIN_SAMPLES = 1 << 28
+
+
+def default_chunks(snum, tnum):
+    """pipeline_chunks=None: the row-chunk pattern for an image of this size."""
+    return DEFAULT_CHUNKS if int(snum) * int(tnum) >= CHUNKING_MIN_SAMPLES else 1
 
 
 def profiles_for_rank(n_profiles, rank, world):
@@ -618,7 +627,7 @@ def _spacing_is_uniform(travel_time_us, dist_km, vel):
 
 
 def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=None, world=None, gather=True,
-                             compute=None, group=None, src=0, pipeline_chunks=DEFAULT_CHUNKS, compute_rows=None, exchange=None,
+                             compute=None, group=None, src=0, pipeline_chunks=None, compute_rows=None, exchange=None,
                              compute_window=None, window_fn=None, peer_image=None):
     """Kirchhoff migration of one radargram over all ranks of the process group.
 
@@ -631,7 +640,8 @@ def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=No
     compute(x, travel_time_us, dist_km, vel, nearfield, x_begin, x_end) -> (snum, x_end-x_begin) tensor;
     defaults to the CUDA kernel (tests on CPU/gloo inject their own), likewise compute_rows (row-range entry) and
     compute_window(win, col0, tnum, tt, dist, vel, nearfield, x_begin, x_end, out, rows) (column-window entry).
-    pipeline_chunks > 1 (a count, or a sequence of relative chunk heights top to bottom): the exchanges and the
+    pipeline_chunks: None = by image size (default_chunks: DEFAULT_CHUNKS from 2^28 samples, one chunk below);
+    > 1 (a count, or a sequence of relative chunk heights top to bottom): the exchanges and the
     kernels overlap in bottom-up row chunks (uniform trace spacing; decided on the host identically on every rank -
     irregular spacing runs the phases back to back).
     peer_image (halo exchange with gather='src'): None = automatic - float32 CUDA images computed by the default
@@ -655,6 +665,8 @@ def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=No
     if rank is None:
         rank = dist.get_rank(group) if dist.is_initialized() else 0
     S, T = x.shape
+    if pipeline_chunks is None:
+        pipeline_chunks = default_chunks(S, T)
     ranges = kirchhoff_output_ranges(T, world, travel_time_us, dist_km, vel)
     xb, xe = ranges[rank]
     if exchange is None:
@@ -709,7 +721,7 @@ def kirchhoff_sharded_device(x, travel_time_us, dist_km, vel, nearfield, rank=No
 
 
 def kirchhoff_sharded_host(data, snum, tnum, travel_time_us, dist_km, vel, nearfield, rank=None, world=None, group=None,
-                           src=0, pipeline_chunks=DEFAULT_CHUNKS):
+                           src=0, pipeline_chunks=None):
     """Host-to-host form of the sharded migration (what a torchrun script calls with the radargram loaded on rank
     `src`): `data` is the (snum, tnum) host array on `src` (None elsewhere); returns the float64 migrated image as a
     host array on `src` (page-locked, like RadarData.migrate's result), None elsewhere."""
