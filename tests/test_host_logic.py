@@ -244,3 +244,31 @@ def test_bench_config_is_the_same_object_for_both_arms():
     c5 = bench.WORKLOADS["kirchhoff_c5"]
     assert c5(args, 0, 1).config()["parallelism"] != c5(args, 0, 8).config()["parallelism"]
     assert "65536" in c5.name and (c5.S, c5.T) == (8192, 65536)
+
+
+def test_kirchhoff_input_window_covers_the_aperture():
+    """impdar_kirchhoff_input_window (host arithmetic of the C library; what the multi-GPU exchange sends a rank): the
+    window must contain every input column an output trace of the range can read - by distance on any monotone geometry
+    (mig_python.py:46-50: 2 r / v <= max(tt)) and by trace count on the fitted uniform grid (the table path reads
+    x +- m for m up to the grid aperture) - start on a multiple of four columns and stay inside the radargram."""
+    import numpy as np
+    from impdar_b200 import migrationlib as ml
+    vel = 1.69e8
+    rng = np.random.default_rng(4)
+    for S, T, dx_m, jitter in [(256, 4000, 0.5, 0.0), (256, 4001, 0.5, 0.3), (512, 3000, 2.0, 0.0), (128, 50, 5.0, 0.2),
+                               (300, 2050, 0.25, 0.0)]:
+        tt_us = np.arange(S) * 0.01 + 0.003
+        d_m = np.arange(T) * dx_m + (jitter * dx_m * (rng.random(T) - 0.5) if jitter else 0.0)
+        d_m = np.sort(d_m)
+        reach = vel * tt_us.max() * 1e-6 / 2.0
+        dxm = (d_m[-1] - d_m[0]) / (T - 1)
+        amax = int(min(T - 1, np.floor(reach / dxm) + 2))
+        for xb, xe in [(0, 1), (0, T), (T // 3, T // 2), (T - 7, T), (5, 6), (T // 2, min(T // 2 + 257, T))]:
+            c0, c1 = ml.kirchhoff_input_window(S, tt_us, d_m / 1e3, vel, xb, xe)
+            assert 0 <= c0 <= xb and xe <= c1 <= T and c0 % 4 == 0 and (c1 % 4 == 0 or c1 == T)
+            near = np.nonzero((d_m >= d_m[xb] - reach) & (d_m <= d_m[xe - 1] + reach))[0]     # by distance
+            assert c0 <= near.min() and near.max() < c1, (S, T, xb, xe)
+            assert c0 <= max(xb - amax, 0) and min(xe - 1 + amax, T - 1) < c1, (S, T, xb, xe)  # by trace count
+            # and it is a window, not the image, whenever the aperture is short against the profile
+            if xe - xb + 2 * amax + 16 < T:
+                assert c1 - c0 < T
