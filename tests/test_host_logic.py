@@ -272,3 +272,32 @@ def test_kirchhoff_input_window_covers_the_aperture():
             # and it is a window, not the image, whenever the aperture is short against the profile
             if xe - xb + 2 * amax + 16 < T:
                 assert c1 - c0 < T
+
+
+def test_sharding_partitions_are_exact():
+    """Output-trace ranges and row chunks of the multi-GPU Kirchhoff (impdar_b200/parallel.py): contiguous, disjoint,
+    covering - whatever the world size, the geometry and the chunk pattern - and the uniform-geometry ranges are equal
+    to within one CTA tile."""
+    import numpy as np
+    from impdar_b200 import parallel
+    rng = np.random.default_rng(8)
+    for T in (7, 40, 4096, 6002, 65536):
+        tt = np.arange(64) * 0.01
+        for jitter in (0.0, 0.4):
+            d = np.arange(T) * 0.005 + (jitter * 0.005 * (rng.random(T) - 0.5) if jitter else 0.0)
+            d = np.sort(d)
+            for world in (1, 2, 3, 4, 8):
+                r = parallel.kirchhoff_output_ranges(T, world, tt, d, 1.69e8)
+                assert len(r) == world and r[0][0] == 0 and r[-1][1] == T
+                assert all(type(v) is int for be in r for v in be)
+                assert all(r[i][1] == r[i + 1][0] and r[i][0] <= r[i][1] for i in range(world - 1))
+                if not jitter and T >= 8 * 256 * world:
+                    w = [e - b for b, e in r]
+                    assert max(w) - min(w) <= 256 and all(b % 256 == 0 for b, _ in r)
+    for S in (1, 5, 24, 1024, 8192):
+        for pattern in (1, 2, 4, 7, 5000, (1, 2, 3, 3, 2, 1), (1, 2, 1), (3.5, 0.25, 1), parallel.DEFAULT_CHUNKS):
+            c = parallel.row_chunks(S, pattern)
+            assert c[0][0] == 0 and c[-1][1] == S and all(c[i][1] == c[i + 1][0] for i in range(len(c) - 1))
+            assert all(b < e for b, e in c) and all(type(v) is int for be in c for v in be)
+    assert parallel.default_chunks(8192, 65536) == parallel.DEFAULT_CHUNKS
+    assert parallel.default_chunks(4096, 16384) == 1
