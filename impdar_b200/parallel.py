@@ -2,10 +2,15 @@
 
 * Independent profiles (the vbp -> hfilt -> Stolt pipeline, any per-profile call) shard round-robin with no
   collective at all: ``profiles_for_rank``.
-* One large Kirchhoff radargram shards by contiguous OUTPUT-trace ranges.  Every output trace needs input
-  traces up to one aperture away, so the input radargram is broadcast once (NCCL over NVLink) and the
-  (snum, range) output blocks are all-gathered.  Ranges are balanced by pair count, not width: traces near
-  the ends of the profile see half an aperture.
+* One large Kirchhoff radargram (the serial trace loop of migrationlib/mig_python.py:35-60) shards by contiguous
+  OUTPUT-trace ranges.  Every output trace needs input traces up to one aperture away: each rank gets the input
+  columns of its range plus one aperture each side (halo exchange) and the finished image lands on the rank that holds
+  the radargram, everything moving and computing bottom-up in row chunks.  Three transports, chosen at run time and
+  identically on every rank: peer-mapped memory (csrc/peer.cu: the kernels store their blocks straight into the
+  holder's image over NVLink, the holder pushes the windows with copy-engine copies, NCCL carries one-element
+  signals), one all_to_all per chunk, or the round-1 scheme (full broadcast + all-gather: every rank ends with the
+  whole image).  Ranges are equal on uniform trace spacing (the table kernels cost per trace) and balanced by pair
+  count otherwise.
 """
 import numpy as np
 
@@ -184,8 +189,9 @@ def _kirchhoff_sharded_halo(x, travel_time_us, dist_km, vel, nearfield, rank, wo
     as they run, a one-element all_reduce per chunk tells src that the chunk's rows are complete everywhere, and src
     copies them into the image it returns on its side stream.  With `peer_in` (a _PeerWindows: every rank's window
     buffer mapped into rank src) the input windows are not packed and sent either: src pushes them as strided 2-D
-    copies over NVLink, one stream per destination, and broadcasts one element per chunk as the "landed" signal.  Returns the (snum, tnum) image on `src` (None
-    elsewhere) for gather == 'src', or this rank's (snum, range) block for gather False."""
+    copies over NVLink, one stream per destination, and broadcasts one element per chunk as the "landed" signal.
+    Returns the (snum, tnum) image on `src` (None elsewhere) for gather == 'src', or this rank's (snum, range) block
+    for gather False."""
     import torch
     import torch.distributed as dist
     S, T = x.shape
